@@ -1,0 +1,267 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (run in the build container only).
+
+TEST INFRASTRUCTURE.  Two fixture files are produced:
+
+* tests/golden/known_answers.npz -- the literal known-answer arrays that the reference's
+  own test-suite holds for the hot path (QGIS / hand-derived tables).  They are
+  extracted by parsing /root/reference/xrspatial/tests/*.py with `ast` and evaluating the
+  fixture functions (no reference source is copied into this repository, only the data).
+* tests/golden/reference_outputs.npz -- seeded inputs and the outputs of the reference's
+  Numba-CPU / NumPy kernels (loaded through oracle/ref_loader.py) on those inputs, for every
+  op on the hot path, including NaN-laden, flat ("water"), integer-valued and odd-shaped cases.
+
+Usage:  python oracle/make_golden.py         (needs /root/reference)
+"""
+import ast
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_loader  # noqa: E402
+
+OUT_DIR = os.path.join(os.path.dirname(HERE), "tests", "golden")
+TESTS = os.path.join(ref_loader.REF_ROOT, "xrspatial", "tests")
+
+
+# ------------------------------------------------------------------ known answers
+def _fixture_funcs(path):
+    src = open(path).read()
+    tree = ast.parse(src)
+    funcs = {}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef):
+            node.decorator_list = []
+            mod = ast.Module(body=[node], type_ignores=[])
+            funcs[node.name] = compile(ast.fix_missing_locations(mod), path, "exec")
+    return funcs
+
+
+def _call(funcs, name, *args, **kw):
+    xr = types.SimpleNamespace(DataArray=lambda a, **k: a)
+    ns = dict(np=np, xr=xr,
+              create_test_raster=lambda data, backend="numpy", **k: np.asarray(data),
+              custom_kernel=lambda k: k,
+              has_dask_array=lambda: False)
+    exec(funcs[name], ns)
+    return ns[name](*args, **kw)
+
+
+def known_answers():
+    g = {}
+    f = _fixture_funcs(os.path.join(TESTS, "conftest.py"))
+    for n in ("elevation_raster", "elevation_raster_no_nans", "raster"):
+        g["conftest." + n] = _call(f, n)
+
+    f = _fixture_funcs(os.path.join(TESTS, "test_slope.py"))
+    g["slope.qgis_slope"] = _call(f, "qgis_slope")
+    f = _fixture_funcs(os.path.join(TESTS, "test_aspect.py"))
+    g["aspect.qgis_aspect"] = _call(f, "qgis_aspect")
+
+    f = _fixture_funcs(os.path.join(TESTS, "test_curvature.py"))
+    for n in ("convex_surface", "concave_surface"):
+        d, e = _call(f, n)
+        g["curvature.%s.data" % n] = np.asarray(d)
+        g["curvature.%s.expected" % n] = np.asarray(e)
+
+    f = _fixture_funcs(os.path.join(TESTS, "test_focal.py"))
+    g["focal.convolve_2d_data"] = _call(f, "convolve_2d_data")
+    g["focal.kernel_circle_1_1_1"] = _call(f, "kernel_circle_1_1_1")
+    g["focal.kernel_annulus_2_2_2_1"] = _call(f, "kernel_annulus_2_2_2_1")
+    g["focal.convolution_kernel_circle_1_1_1"] = _call(f, "convolution_kernel_circle_1_1_1")
+    g["focal.convolution_kernel_annulus_2_2_1"] = _call(f, "convolution_kernel_annulus_2_2_1")
+    k, e = _call(f, "convolution_custom_kernel")
+    g["focal.convolution_custom_kernel.kernel"] = k
+    g["focal.convolution_custom_kernel.expected"] = e
+    d, k, e = _call(f, "data_apply")
+    g["focal.data_apply.data"], g["focal.data_apply.kernel"] = d, k
+    d, k, e = _call(f, "data_focal_stats")
+    g["focal.data_focal_stats.data"] = d
+    g["focal.data_focal_stats.kernel"] = k
+    g["focal.data_focal_stats.expected"] = e  # order: mean max min range std var sum
+
+    f = _fixture_funcs(os.path.join(TESTS, "test_multispectral.py"))
+    for n in ("blue", "green", "red", "nir", "tir", "swir1", "swir2"):
+        g["multispectral.%s_data" % n] = np.asarray(_call(f, n + "_data", "numpy"), dtype=np.float64)
+    for n in ("arvi", "evi", "nbr", "nbr2", "ndvi", "ndmi", "savi", "gci", "sipi", "ebbi"):
+        g["multispectral.qgis_" + n] = _call(f, "qgis_" + n)
+    for n in ("normalized_ratio", "arvi", "evi", "savi", "sipi", "ebbi"):
+        vals = _call(f, "data_uint_dtype_" + n, np.uint16)
+        for i, v in enumerate(vals):
+            g["multispectral.uint_%s.%d" % (n, i)] = np.asarray(v)
+
+    f = _fixture_funcs(os.path.join(TESTS, "test_zonal.py"))
+    g["zonal.data_zones"] = _call(f, "data_zones", "numpy")
+    g["zonal.data_values_2d"] = _call(f, "data_values_2d", "numpy")
+    for n in ("result_default_stats", "qgis_zonal_stats"):
+        d = _call(f, n)
+        for k2, v in d.items():
+            g["zonal.%s.%s" % (n, k2)] = np.asarray(v, dtype=np.float64)
+    zid, d = _call(f, "result_zone_ids_stats")
+    g["zonal.result_zone_ids_stats.zone_ids"] = np.asarray(zid)
+    for k2, v in d.items():
+        g["zonal.result_zone_ids_stats.%s" % k2] = np.asarray(v, dtype=np.float64)
+    g["zonal.result_default_stats_dataarray"] = _call(f, "result_default_stats_dataarray")
+    return g
+
+
+# ------------------------------------------------------------------ reference outputs
+def terrain(rng, h, w, water=False, nans=0.0, integer=False):
+    """Small smooth-ish synthetic DEM (double cumulative sum of noise + a ramp)."""
+    z = rng.standard_normal((h, w)).cumsum(0).cumsum(1)
+    z += np.linspace(0, 30, w)[None, :] + np.linspace(0, 10, h)[:, None]
+    z = (z - z.min()) / (z.max() - z.min() + 1e-9) * 4000.0
+    if water:
+        z[z < 0.3 * z.max()] = 0.0
+    if integer:
+        z = np.round(z)
+    z = z.astype(np.float32)
+    if nans:
+        m = rng.random((h, w)) < nans
+        z[m] = np.nan
+    return z
+
+
+def reference_outputs():
+    slope = ref_loader.load("slope")
+    aspect = ref_loader.load("aspect")
+    curv = ref_loader.load("curvature")
+    hill = ref_loader.load("hillshade")
+    conv = ref_loader.load("convolution")
+    focal = ref_loader.load("focal")
+    ms = ref_loader.load("multispectral")
+    zonal = ref_loader.load("zonal")
+
+    g = {}
+    rng = np.random.default_rng(20260922)
+    cases = {
+        "smooth": terrain(rng, 37, 53),
+        "water": terrain(rng, 41, 36, water=True),
+        "nans": terrain(rng, 33, 47, nans=0.03),
+        "integer": terrain(rng, 20, 64, integer=True),
+        "rough": (rng.random((29, 31)) * 1000).astype(np.float32),
+        "tiny": (rng.integers(-100, 100, size=(3, 4))).astype(np.float32),
+        "rand_2x4": np.random.default_rng(2841).integers(-100, 100, size=(2, 4)).astype(np.float32),
+        "rand_10x15": np.random.default_rng(2841).integers(-100, 100, size=(10, 15)).astype(np.float32),
+    }
+    for name, z in cases.items():
+        g["dem.%s" % name] = z
+        g["slope.%s" % name] = slope._cpu(z, 30.0, 30.0)
+        g["slope_aniso.%s" % name] = slope._cpu(z, 10.0, 25.5)
+        g["aspect.%s" % name] = aspect._run_numpy(z)
+        g["curvature.%s" % name] = curv._run_numpy(z, 30.0)
+        g["hillshade.%s" % name] = hill._run_numpy(z, 225, 25)
+        g["hillshade_az315_alt45.%s" % name] = hill._run_numpy(z, 315, 45)
+        g["focal_mean.%s" % name] = focal._mean_numpy(z.astype(float), (np.nan,))
+        out = z.astype(float)
+        for _ in range(3):
+            out = focal._mean_numpy(out, (np.nan,))
+        g["focal_mean_p3.%s" % name] = out
+        g["focal_mean_ex.%s" % name] = focal._mean_numpy(z.astype(float), (np.nan, 0.0))
+
+    # convolution kernels
+    kernels = {
+        "box3": np.ones((3, 3)) / 9.0,
+        "box9": np.ones((9, 9)) / 81.0,
+        "mixed5": rng.standard_normal((5, 5)),
+        "mixed3x7": rng.standard_normal((3, 7)),
+        "mixed25": rng.standard_normal((25, 25)),
+        "int3": np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]]),
+    }
+    zc = terrain(rng, 61, 75)
+    zcn = zc.copy()
+    zcn[10, 12] = np.nan
+    zcn[40, 70] = np.inf
+    g["conv.dem"] = zc
+    g["conv.dem_nan"] = zcn
+    for kn, k in kernels.items():
+        g["conv.kernel.%s" % kn] = np.asarray(k, dtype=np.float64)
+        g["conv.out.%s" % kn] = conv._convolve_2d_numpy(zc, k)
+        g["conv.out_nan.%s" % kn] = conv._convolve_2d_numpy(zcn, k)
+
+    # focal apply / focal_stats
+    masks = {
+        "circle3": np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]], dtype=float),
+        "full3": np.ones((3, 3)),
+        "annulus5": np.array([[0, 1, 1, 1, 0], [1, 1, 0, 1, 1], [1, 0, 0, 0, 1],
+                              [1, 1, 0, 1, 1], [0, 1, 1, 1, 0]], dtype=float),
+        "rect3x5": np.ones((3, 5)),
+        "weights3": np.array([[1, 2, 0], [0.5, 1, 0], [0, 0, 1]], dtype=float),
+    }
+    fn = dict(mean=focal._calc_mean, sum=focal._calc_sum, min=focal._calc_min,
+              max=focal._calc_max, std=focal._calc_std, range=focal._calc_range,
+              var=focal._calc_var)
+    za = terrain(rng, 23, 27, nans=0.05)
+    g["apply.dem"] = za
+    for mn, m in masks.items():
+        g["apply.mask.%s" % mn] = m
+        for sn, f in fn.items():
+            g["apply.out.%s.%s" % (mn, sn)] = focal._apply_numpy(za, m, f)
+
+    # multispectral
+    def band(lo=0.02, hi=0.6):
+        b = terrain(rng, 31, 45)
+        b = lo + (hi - lo) * b / 4000.0
+        return b.astype(np.float32)
+
+    nir, red, blue, green, swir, tir = [band() for _ in range(6)]
+    for b in (nir, red, blue, green, swir, tir):
+        b[rng.random(b.shape) < 0.02] = 0.0
+        b[rng.random(b.shape) < 0.01] = np.nan
+    red[5, 5], nir[5, 5] = 0.25, -0.25      # denominator exactly 0
+    g.update({"ms.nir": nir, "ms.red": red, "ms.blue": blue, "ms.green": green,
+              "ms.swir": swir, "ms.tir": tir})
+    g["ms.ndvi"] = ms._normalized_ratio_cpu(nir, red)
+    g["ms.savi"] = ms._savi_cpu(nir, red, 1.0)
+    g["ms.savi_L05"] = ms._savi_cpu(nir, red, 0.5)
+    g["ms.evi"] = ms._evi_cpu(nir, red, blue, 6.0, 7.5, 1.0, 2.5)
+    g["ms.arvi"] = ms._arvi_cpu(nir, red, blue)
+    g["ms.gci"] = ms._gci_cpu(nir, green)
+    g["ms.sipi"] = ms._sipi_cpu(nir, red, blue)
+    g["ms.ebbi"] = ms._ebbi_cpu(red, swir, tir)
+
+    # zonal.stats: float32 values / int32 zones, float64 values / float zones with NaN
+    stats7 = ["mean", "max", "min", "sum", "std", "var", "count"]
+    zv = terrain(rng, 48, 64, nans=0.02)
+    zz = ((np.arange(48)[:, None] // 12) * 4 + (np.arange(64)[None, :] // 16)).astype(np.int32)
+    zz[rng.random(zz.shape) < 0.1] = 100 + rng.integers(0, 5)
+    g["zonal.values_f32"], g["zonal.zones_i32"] = zv, zz
+    df = zonal._stats_numpy(zz, zv, None, {s: zonal._DEFAULT_STATS[s] for s in stats7 + ["majority"]},
+                            None, return_type="pandas.DataFrame")
+    for c in df.columns:
+        g["zonal.f32_i32.%s" % c] = np.asarray(df[c])
+    df = zonal._stats_numpy(zz, zv, [3, 7, 100, 999], {s: zonal._DEFAULT_STATS[s] for s in stats7},
+                            0.0, return_type="pandas.DataFrame")
+    for c in df.columns:
+        g["zonal.f32_i32_ids_nodata.%s" % c] = np.asarray(df[c])
+    zv64 = (zv.astype(np.float64) + 1e6) * 1.000001
+    zzf = zz.astype(np.float64)
+    zzf[0, :7] = np.nan
+    zzf[1, 3] = -2.5
+    g["zonal.values_f64"], g["zonal.zones_f64"] = zv64, zzf
+    df = zonal._stats_numpy(zzf, zv64, None, {s: zonal._DEFAULT_STATS[s] for s in stats7},
+                            None, return_type="pandas.DataFrame")
+    for c in df.columns:
+        g["zonal.f64_f64.%s" % c] = np.asarray(df[c])
+    arr = zonal._stats_numpy(zz, zv, [3, 7], {s: zonal._DEFAULT_STATS[s] for s in ("mean", "count")},
+                             None, return_type="xarray.DataArray")
+    g["zonal.f32_i32.broadcast_mean_count_3_7"] = arr
+    return g
+
+
+def main():
+    os.makedirs(OUT_DIR, exist_ok=True)
+    ka = known_answers()
+    np.savez_compressed(os.path.join(OUT_DIR, "known_answers.npz"), **ka)
+    ro = reference_outputs()
+    np.savez_compressed(os.path.join(OUT_DIR, "reference_outputs.npz"), **ro)
+    for n in ("known_answers.npz", "reference_outputs.npz"):
+        print(n, os.path.getsize(os.path.join(OUT_DIR, n)), "bytes")
+    print(len(ka), "known-answer arrays;", len(ro), "reference input/output arrays")
+
+
+if __name__ == "__main__":
+    main()

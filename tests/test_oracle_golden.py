@@ -1,0 +1,212 @@
+"""Pins the CPU oracle (oracle/xrs_oracle.c, oracle/oracle.py) against
+
+(a) the known-answer arrays of the reference's own test-suite (tests/golden/known_answers.npz,
+    extracted from /root/reference/xrspatial/tests by oracle/make_golden.py) and
+(b) outputs of the unmodified reference kernels on seeded inputs
+    (tests/golden/reference_outputs.npz).
+
+CPU only; runs in seconds.
+"""
+import numpy as np
+import pytest
+
+import oracle as o
+
+DEMS = ["smooth", "water", "nans", "integer", "rough", "tiny", "rand_2x4", "rand_10x15"]
+STATS = ["mean", "max", "min", "range", "std", "var", "sum"]
+
+
+def same_nan(a, b):
+    np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
+
+
+# ----------------------------------------------------------------- (a) known answers
+def test_slope_qgis(known):
+    # test_slope.py:22-49 (res=(1,1), interior compared at rtol 1e-5)
+    out = o.slope(known["conftest.elevation_raster"], 1, 1)
+    np.testing.assert_allclose(out[1:-1, 1:-1], known["slope.qgis_slope"][1:-1, 1:-1],
+                               rtol=1e-5, equal_nan=True)
+    assert out.dtype == np.float32
+    assert np.isnan(out[0]).all() and np.isnan(out[-1]).all()
+    assert np.isnan(out[:, 0]).all() and np.isnan(out[:, -1]).all()
+
+
+def test_slope_docstring():
+    # slope.py:317-331
+    data = np.array([[0, 0, 0, 0, 0], [0, 0, 0, -1, 2], [0, 0, 0, 0, 1], [0, 0, 0, 5, 0]])
+    exp = np.array([[0., 14.036243, 32.512516], [0., 42.031113, 53.395725]], dtype=np.float32)
+    np.testing.assert_allclose(o.slope(data, 1, 1)[1:3, 1:4], exp, rtol=1e-6)
+
+
+def test_aspect_qgis(known):
+    # test_aspect.py:19-47
+    out = o.aspect(known["conftest.elevation_raster"])
+    np.testing.assert_allclose(out[1:-1, 1:-1], known["aspect.qgis_aspect"][1:-1, 1:-1],
+                               rtol=1e-5, equal_nan=True)
+
+
+@pytest.mark.parametrize("surf", ["convex_surface", "concave_surface"])
+def test_curvature_known(known, surf):
+    # test_curvature.py:26-84 (res (1,1) -> cellsize 1)
+    out = o.curvature(known["curvature.%s.data" % surf], 1)
+    np.testing.assert_allclose(out, known["curvature.%s.expected" % surf], equal_nan=True)
+
+
+def test_curvature_flat():
+    out = o.curvature(np.zeros((5, 7)), 1)
+    assert (out[1:-1, 1:-1] == 0).all() and np.signbit(out[1:-1, 1:-1]).all()  # -0.0
+
+
+def test_hillshade_docstring():
+    # hillshade.py:153-170 (the only numeric pin the reference has for hillshade)
+    data = np.array([[0., 0., 0., 0., 0.], [0., 1., 0., 2., 0.], [0., 0., 3., 0., 0.],
+                     [0., 0., 0., 0., 0.], [0., 0., 0., 0., 0.]])
+    exp = np.array([[0.71130913, 0.44167341, 0.71130913],
+                    [0.95550163, 0.71130913, 0.52478473],
+                    [0.71130913, 0.88382559, 0.71130913]])
+    np.testing.assert_allclose(o.hillshade(data)[1:4, 1:4], exp, rtol=1e-6)
+
+
+def test_convolution_known(known):
+    # test_focal.py:113-225
+    data = known["focal.convolve_2d_data"]
+    for k, e in (("focal.kernel_circle_1_1_1", "focal.convolution_kernel_circle_1_1_1"),
+                 ("focal.kernel_annulus_2_2_2_1", "focal.convolution_kernel_annulus_2_2_1"),
+                 ("focal.convolution_custom_kernel.kernel", "focal.convolution_custom_kernel.expected")):
+        np.testing.assert_allclose(o.convolve_2d(data, known[k]), known[e], equal_nan=True)
+
+
+def test_focal_stats_known(known):
+    # test_focal.py:353-404
+    data, kernel = known["focal.data_focal_stats.data"], known["focal.data_focal_stats.kernel"]
+    exp = known["focal.data_focal_stats.expected"]
+    for i, s in enumerate(STATS):
+        np.testing.assert_allclose(o.focal_apply(data, kernel, s), exp[i], rtol=1e-6, err_msg=s)
+
+
+def test_focal_mean_docstring():
+    # focal.py:195-209
+    data = np.array([[0., 0., 0., 0., 0.], [0., 1., 1., 1., 0.], [0., 1., 1., 1., 0.],
+                     [0., 1., 1., 1., 0.], [0., 0., 0., 0., 0.]])
+    out = o.focal_mean(data)
+    assert out.dtype == np.float64
+    np.testing.assert_allclose(out[0, :3], [0.25, 0.33333333, 0.5], rtol=1e-7)
+    np.testing.assert_allclose(out[2, 2], 1.0)
+
+
+MS_QGIS = {
+    "ndvi": ("normalized_ratio", ("nir", "red")), "nbr": ("normalized_ratio", ("nir", "swir2")),
+    "nbr2": ("normalized_ratio", ("swir1", "swir2")), "ndmi": ("normalized_ratio", ("nir", "swir1")),
+    "savi": ("savi", ("nir", "red")), "evi": ("evi", ("nir", "red", "blue")),
+    "arvi": ("arvi", ("nir", "red", "blue")), "gci": ("gci", ("nir", "green")),
+    "sipi": ("sipi", ("nir", "red", "blue")), "ebbi": ("ebbi", ("red", "swir1", "tir")),
+}
+
+
+@pytest.mark.parametrize("name", sorted(MS_QGIS))
+def test_multispectral_qgis(known, name):
+    # test_multispectral.py:12-283, compared like general_output_checks (rtol 1e-6 default
+    # there is loosened by the QGIS tables' 7-8 significant digits -> rtol 1e-5)
+    fn, bands = MS_QGIS[name]
+    out = getattr(o, fn)(*[known["multispectral.%s_data" % b] for b in bands])
+    np.testing.assert_allclose(out, known["multispectral.qgis_" + name], rtol=1e-5, atol=1e-7,
+                               equal_nan=True)
+
+
+def test_multispectral_uint(known):
+    # test_multispectral.py:285-338
+    g = lambda n, i: known["multispectral.uint_%s.%d" % (n, i)]  # noqa: E731
+    np.testing.assert_allclose(o.normalized_ratio(g("normalized_ratio", 0), g("normalized_ratio", 1)),
+                               g("normalized_ratio", 2), rtol=1e-6)
+    np.testing.assert_allclose(o.arvi(g("arvi", 0), g("arvi", 1), g("arvi", 2)), g("arvi", 3), rtol=1e-6)
+    np.testing.assert_allclose(o.evi(g("evi", 0), g("evi", 1), g("evi", 2)), g("evi", 3), rtol=1e-6)
+    np.testing.assert_allclose(o.savi(g("savi", 0), g("savi", 1)), g("savi", 2), rtol=1e-6)
+    np.testing.assert_allclose(o.sipi(g("sipi", 0), g("sipi", 1), g("sipi", 2)), g("sipi", 3), rtol=1e-6)
+    np.testing.assert_allclose(o.ebbi(g("ebbi", 0), g("ebbi", 1), g("ebbi", 2)), g("ebbi", 3), rtol=1e-6)
+
+
+def test_zonal_known(known):
+    # test_zonal.py:30-75, 131-146, 339-385, 593-602
+    zones, values = known["zonal.data_zones"], known["zonal.data_values_2d"]
+    res = o.zonal_stats(zones, values, stats_funcs=["mean", "max", "min", "sum", "std", "var", "count", "majority"])
+    for k in ("zone", "mean", "max", "min", "sum", "std", "var", "count", "majority"):
+        np.testing.assert_allclose(res[k], known["zonal.result_default_stats." + k], rtol=1e-5, atol=1e-7)
+    res = o.zonal_stats(zones, values, zone_ids=list(known["zonal.result_zone_ids_stats.zone_ids"]))
+    for k in ("zone", "mean", "max", "min", "sum", "std", "var", "count"):
+        np.testing.assert_allclose(res[k], known["zonal.result_zone_ids_stats." + k], rtol=1e-5, atol=1e-7)
+    res = o.zonal_stats(known["conftest.raster"], known["conftest.elevation_raster_no_nans"],
+                        stats_funcs=["mean", "max", "min", "sum", "count"])
+    for k in ("zone", "mean", "max", "min", "sum", "count"):
+        np.testing.assert_allclose(res[k], known["zonal.qgis_zonal_stats." + k], rtol=1e-5, atol=1e-5)
+
+
+# --------------------------------------------------- (b) outputs of the reference itself
+@pytest.mark.parametrize("case", DEMS)
+def test_surface_vs_reference(refout, case):
+    z = refout["dem." + case]
+    # f64 arithmetic restated exactly -> identical after rounding to f32
+    np.testing.assert_array_equal(o.slope(z, 30.0, 30.0), refout["slope." + case])
+    np.testing.assert_array_equal(o.slope(z, 10.0, 25.5), refout["slope_aniso." + case])
+    np.testing.assert_array_equal(o.aspect(z), refout["aspect." + case])
+    np.testing.assert_array_equal(o.curvature(z, 30.0), refout["curvature." + case])
+    # NumPy's SIMD float32 transcendentals vs libm: a few f32 ulp on values in [0, 1]
+    np.testing.assert_allclose(o.hillshade(z, 225, 25), refout["hillshade." + case],
+                               rtol=0, atol=5e-7, equal_nan=True)
+    np.testing.assert_allclose(o.hillshade(z, 315, 45), refout["hillshade_az315_alt45." + case],
+                               rtol=0, atol=5e-7, equal_nan=True)
+
+
+@pytest.mark.parametrize("case", DEMS)
+def test_focal_mean_vs_reference(refout, case):
+    z = refout["dem." + case]
+    np.testing.assert_array_equal(o.focal_mean(z), refout["focal_mean." + case])
+    np.testing.assert_array_equal(o.focal_mean(z, passes=3), refout["focal_mean_p3." + case])
+    np.testing.assert_array_equal(o.focal_mean(z, excludes=(np.nan, 0.0)), refout["focal_mean_ex." + case])
+
+
+@pytest.mark.parametrize("kn", ["box3", "box9", "mixed5", "mixed3x7", "mixed25", "int3"])
+def test_convolve_vs_reference(refout, kn):
+    k = refout["conv.kernel." + kn]
+    np.testing.assert_array_equal(o.convolve_2d(refout["conv.dem"], k), refout["conv.out." + kn])
+    np.testing.assert_array_equal(o.convolve_2d(refout["conv.dem_nan"], k), refout["conv.out_nan." + kn])
+
+
+@pytest.mark.parametrize("mn", ["circle3", "full3", "annulus5", "rect3x5", "weights3"])
+def test_focal_apply_vs_reference(refout, mn):
+    for s in STATS:
+        np.testing.assert_array_equal(o.focal_apply(refout["apply.dem"], refout["apply.mask." + mn], s),
+                                      refout["apply.out.%s.%s" % (mn, s)], err_msg=s)
+
+
+def test_multispectral_vs_reference(refout):
+    r = refout
+    np.testing.assert_array_equal(o.normalized_ratio(r["ms.nir"], r["ms.red"]), r["ms.ndvi"])
+    np.testing.assert_array_equal(o.savi(r["ms.nir"], r["ms.red"], 1.0), r["ms.savi"])
+    np.testing.assert_array_equal(o.savi(r["ms.nir"], r["ms.red"], 0.5), r["ms.savi_L05"])
+    np.testing.assert_array_equal(o.evi(r["ms.nir"], r["ms.red"], r["ms.blue"]), r["ms.evi"])
+    np.testing.assert_array_equal(o.arvi(r["ms.nir"], r["ms.red"], r["ms.blue"]), r["ms.arvi"])
+    np.testing.assert_array_equal(o.gci(r["ms.nir"], r["ms.green"]), r["ms.gci"])
+    np.testing.assert_array_equal(o.sipi(r["ms.nir"], r["ms.red"], r["ms.blue"]), r["ms.sipi"])
+    np.testing.assert_array_equal(o.ebbi(r["ms.red"], r["ms.swir"], r["ms.tir"]), r["ms.ebbi"])
+
+
+def test_zonal_vs_reference(refout):
+    r = refout
+    cols = ["zone", "mean", "max", "min", "sum", "std", "var", "count"]
+    res = o.zonal_stats(r["zonal.zones_i32"], r["zonal.values_f32"],
+                        stats_funcs=cols[1:] + ["majority"])
+    for c in cols + ["majority"]:
+        np.testing.assert_array_equal(res[c], r["zonal.f32_i32." + c], err_msg=c)
+    res = o.zonal_stats(r["zonal.zones_i32"], r["zonal.values_f32"], zone_ids=[3, 7, 100, 999],
+                        nodata_values=0.0)
+    for c in cols:
+        np.testing.assert_array_equal(res[c], r["zonal.f32_i32_ids_nodata." + c], err_msg=c)
+    res = o.zonal_stats(r["zonal.zones_f64"], r["zonal.values_f64"])
+    for c in cols:
+        np.testing.assert_array_equal(res[c], r["zonal.f64_f64." + c], err_msg=c)
+
+
+def test_threads_do_not_change_results(refout):
+    z = refout["dem.smooth"]
+    np.testing.assert_array_equal(o.slope(z, 30, 30, nthreads=4), o.slope(z, 30, 30))
+    np.testing.assert_array_equal(o.focal_mean(z, nthreads=4), o.focal_mean(z))
