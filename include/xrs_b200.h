@@ -1,0 +1,195 @@
+/*
+ * xrs_b200.h -- C ABI of libxrs_b200.so, the B200 (sm_100a) backend for the dense 2-D
+ * stencil hot path of xarray-spatial.
+ *
+ * The reference has no FFI: its backend seam is the set of Python runner callables that
+ * xrspatial.utils.ArrayTypeFunctionMapping (utils.py:117-143) selects by array type, e.g.
+ * slope._run_cupy(data, cellsize_x, cellsize_y) (slope.py:145).  Each entry point below is
+ * what a fifth, "b200" runner of that mapping binds through ctypes; the comment on every
+ * function names the reference runner it replaces (file:line in /root/reference/xrspatial).
+ * INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *  - plain C types only; rasters are row-major (H rows = y, W cols = x); pitches in BYTES.
+ *  - `*_f32` device entry points take DEVICE pointers and a cudaStream_t (as void*), only
+ *    enqueue work on that stream and never synchronise or allocate user-visible memory.
+ *  - `xrs_host_*` entry points take HOST pointers (pinned or pageable), run the same kernels
+ *    through an internal pipelined H2D / compute / D2H stripe engine, and return when the
+ *    result is in `out`.  They are what a numpy-backed DataArray call uses.
+ *  - return value: 0 on success, negative xrs_status otherwise; xrs_last_error_string()
+ *    describes the last failure on the calling thread.  Nothing throws across the ABI.
+ *  - inputs are never modified.
+ */
+#ifndef XRS_B200_H
+#define XRS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XRS_ABI_VERSION 1
+
+typedef void *xrs_stream_t; /* cudaStream_t */
+
+enum xrs_status {
+    XRS_OK = 0,
+    XRS_EINVAL = -1,       /* bad argument (shape, null pointer, even kernel, ...) */
+    XRS_ECUDA = -2,        /* CUDA runtime / driver error */
+    XRS_EUNSUPPORTED = -3, /* valid request this build cannot serve */
+    XRS_ENOMEM = -4
+};
+
+/* focal statistic ids (focal.py:782-790 `_function_mapping`) */
+enum xrs_focal_stat {
+    XRS_STAT_MEAN = 0, XRS_STAT_SUM = 1, XRS_STAT_MIN = 2, XRS_STAT_MAX = 3,
+    XRS_STAT_STD = 4, XRS_STAT_RANGE = 5, XRS_STAT_VAR = 6
+};
+
+/* element types for zonal inputs */
+enum xrs_dtype { XRS_F32 = 0, XRS_F64 = 1, XRS_I32 = 2, XRS_I64 = 3 };
+
+int xrs_abi_version(void);
+const char *xrs_last_error_string(void);
+/* device 0..n-1 properties the Python layer needs to size launches / report rooflines */
+int xrs_device_count(int *n);
+int xrs_device_sm_count(int device, int *sm_count);
+
+/* ------------------------------------------------------------------ surface (3x3)
+ * All: in/out float32, 1-cell NaN ring, NaN inputs propagate to their 3x3 neighbourhood. */
+
+/* slope._run_cupy (slope.py:145-160) / `_cpu` (slope.py:56-76): Horn slope in degrees. */
+int xrs_slope_f32(const float *in, int64_t in_pitch, float *out, int64_t out_pitch,
+                  int64_t H, int64_t W, double cellsize_x, double cellsize_y, xrs_stream_t s);
+/* aspect._run_cupy (aspect.py:139-147) / `_run_numpy` (aspect.py:56-90): compass degrees,
+ * -1 on flats; follows the CPU path (no 359.999 clamp). */
+int xrs_aspect_f32(const float *in, int64_t in_pitch, float *out, int64_t out_pitch,
+                   int64_t H, int64_t W, xrs_stream_t s);
+/* curvature._run_cupy (curvature.py:81-95) / `_cpu` (curvature.py:31-41). */
+int xrs_curvature_f32(const float *in, int64_t in_pitch, float *out, int64_t out_pitch,
+                      int64_t H, int64_t W, double cellsize, xrs_stream_t s);
+/* hillshade._run_cupy (hillshade.py:78-100) / `_run_numpy` (hillshade.py:20-35);
+ * output float32 as the reference's GPU path and docs promise. */
+int xrs_hillshade_f32(const float *in, int64_t in_pitch, float *out, int64_t out_pitch,
+                      int64_t H, int64_t W, double azimuth, double angle_altitude,
+                      xrs_stream_t s);
+/* analytics.summarize_terrain (analytics.py:84-86) fused: one read, up to four writes.
+ * Any output pointer may be NULL (that product is skipped); all outputs share out_pitch. */
+int xrs_surface_suite_f32(const float *in, int64_t in_pitch, float *slope_out,
+                          float *aspect_out, float *curvature_out, float *hillshade_out,
+                          int64_t out_pitch, int64_t H, int64_t W, double cellsize_x,
+                          double cellsize_y, double azimuth, double angle_altitude,
+                          xrs_stream_t s);
+
+/* ------------------------------------------------------------------ focal / convolution */
+/* focal._mean_cupy (focal.py:135-146) / `_mean_numpy` (focal.py:44-67): ONE pass of the 3x3
+ * NaN-skipping mean with clamped windows; centre cells equal (NaN-aware) to one of
+ * `excludes` (host array, n_ex <= 8) are copied through.  f32: float in/out (sums in f64);
+ * f64: double in/out.  in and out must not alias. */
+int xrs_focal_mean_f32(const float *in, int64_t in_pitch, float *out, int64_t out_pitch,
+                       int64_t H, int64_t W, const double *excludes, int n_ex, xrs_stream_t s);
+int xrs_focal_mean_f64(const double *in, int64_t in_pitch, double *out, int64_t out_pitch,
+                       int64_t H, int64_t W, const double *excludes, int n_ex, xrs_stream_t s);
+/* convolution._convolve_2d_cupy (convolution.py:368-374) / `_convolve_2d_numpy` (:285-313):
+ * correlation with a host float64 kernel (kh, kw odd, <= 63); NaN ring of (kh/2, kw/2). */
+int xrs_convolve2d_f32(const float *in, int64_t in_pitch, float *out, int64_t out_pitch,
+                       int64_t H, int64_t W, const double *kernel, int kh, int kw,
+                       xrs_stream_t s);
+/* focal._focal_stats_cupy (focal.py:757-779) with the CPU semantics of `_apply_numpy`
+ * (focal.py:305-326) + reducers (:268-302): cells where kernel == 1 participate, NaN and
+ * out-of-raster cells are skipped.  `stat` is an xrs_focal_stat. */
+int xrs_focal_stat_f32(const float *in, int64_t in_pitch, float *out, int64_t out_pitch,
+                       int64_t H, int64_t W, const double *kernel, int kh, int kw, int stat,
+                       xrs_stream_t s);
+
+/* ------------------------------------------------------------------ multispectral
+ * Elementwise over n contiguous float32 cells; out is NaN where the denominator is 0. */
+/* multispectral._run_normalized_ratio_cupy (:862) -- ndvi, nbr, nbr2, ndmi */
+int xrs_normalized_ratio_f32(const float *a, const float *b, float *out, int64_t n, xrs_stream_t s);
+/* multispectral._savi_cupy (:912) */
+int xrs_savi_f32(const float *nir, const float *red, double soil_factor, float *out, int64_t n,
+                 xrs_stream_t s);
+/* multispectral._evi_cupy (:210) */
+int xrs_evi_f32(const float *nir, const float *red, const float *blue, double c1, double c2,
+                double soil_factor, double gain, float *out, int64_t n, xrs_stream_t s);
+/* multispectral._arvi_cupy (:65) */
+int xrs_arvi_f32(const float *nir, const float *red, const float *blue, float *out, int64_t n,
+                 xrs_stream_t s);
+/* multispectral._gci_cupy (:378) */
+int xrs_gci_f32(const float *nir, const float *green, float *out, int64_t n, xrs_stream_t s);
+/* multispectral._sipi_cupy (:1052) */
+int xrs_sipi_f32(const float *nir, const float *red, const float *blue, float *out, int64_t n,
+                 xrs_stream_t s);
+/* multispectral._ebbi_cupy (:1195) */
+int xrs_ebbi_f32(const float *red, const float *swir, const float *tir, float *out, int64_t n,
+                 xrs_stream_t s);
+
+/* ------------------------------------------------------------------ zonal.stats
+ * zonal._stats_cupy (zonal.py:335-419) / `_stats_numpy` (:280-332) replaced by one scan that
+ * accumulates per-zone partials; mean/std/var are finalised from them by the caller, and
+ * partials from several devices combine with sum / min / max (NCCL AllReduce).
+ *
+ * zones (zones_dtype: I32, I64, F32, F64) and values (values_dtype: F32, F64, I32, I64) are
+ * device arrays of n cells.  `zone_ids` is a DEVICE array of nz sorted unique ids as float64;
+ * a cell contributes to the zone whose id equals its zone value, if its value is finite and
+ * != nodata (when has_nodata).  Outputs (device, length nz, caller-zeroed/initialised by
+ * xrs_zonal_init): count (int64), sum, sumsq of (v - pivot[z]) (float64), min, max
+ * (float64).  pivot is a DEVICE float64 array of nz (a per-zone shift, any finite value in
+ * the zone's range; identical on all devices) that keeps sumsq well conditioned. */
+int xrs_zonal_init(int64_t *count, double *sum, double *sumsq, double *vmin, double *vmax,
+                   int nz, xrs_stream_t s);
+int xrs_zonal_partials(const void *values, int values_dtype, const void *zones,
+                       int zones_dtype, int64_t n, const double *zone_ids, int nz,
+                       const double *pivot, int has_nodata, double nodata, int64_t *count,
+                       double *sum, double *sumsq, double *vmin, double *vmax,
+                       xrs_stream_t s);
+/* same, with a hint for integer zone rasters whose ids all lie in
+ * [lut_base, lut_base + 8192): use_lut != 0 replaces the binary search of zone_ids by a
+ * direct shared-memory table. */
+int xrs_zonal_partials_ex(const void *values, int values_dtype, const void *zones,
+                          int zones_dtype, int64_t n, const double *zone_ids, int nz,
+                          const double *pivot, int has_nodata, double nodata, int use_lut,
+                          int64_t lut_base, int64_t *count, double *sum, double *sumsq,
+                          double *vmin, double *vmax, xrs_stream_t s);
+
+/* ------------------------------------------------------------------ host-buffer (end-to-end)
+ * Same operators on HOST rasters: the library stripes the raster over rows, and overlaps
+ * host->device copies, kernels and device->host copies on internal streams.  `op` selects
+ * the operator; scalar parameters are passed in p[0..7] in the order of the device entry
+ * point (e.g. slope: p[0]=cellsize_x, p[1]=cellsize_y).  aux/naux carry the excludes
+ * (focal mean) or the kernel followed by kh,kw in p[0],p[1] (convolve / focal stat). */
+enum xrs_op {
+    XRS_OP_SLOPE = 0, XRS_OP_ASPECT = 1, XRS_OP_CURVATURE = 2, XRS_OP_HILLSHADE = 3,
+    XRS_OP_FOCAL_MEAN = 4, XRS_OP_CONVOLVE = 5, XRS_OP_FOCAL_STAT = 6,
+    XRS_OP_FOCAL_MEAN_F64 = 7 /* in/out are double */
+};
+/* in/out: float32 rasters (float64 for XRS_OP_FOCAL_MEAN_F64), contiguous rows.
+ * p: slope {csx, csy}; curvature {cellsize}; hillshade {azimuth, altitude};
+ *    convolve {kh, kw}; focal stat {kh, kw, stat}.  aux: excludes / kernel (host). */
+int xrs_host_stencil(int op, const void *in, void *out, int64_t H, int64_t W, const double *p,
+                     const double *aux, int naux, int device);
+/* frees the per-device staging buffers the host path keeps between calls */
+int xrs_host_release(int device);
+/* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers that want
+ * full-speed DMA on the host path */
+int xrs_host_alloc(void **ptr, int64_t bytes);
+int xrs_host_free(void *ptr);
+
+/* test / profiling hooks: did the last stencil launch on this thread use the TMA kernel,
+ * and with how many CTAs */
+int xrs_debug_last_used_tma(void);
+int xrs_debug_last_grid(void);
+
+/* ------------------------------------------------------------------ synthetic inputs
+ * Deterministic fBm-like terrain (value-noise octaves), a pure function of
+ * (seed, global row, global col): stripes generated on different devices tile exactly.
+ * Used by bench.py and the tests; not part of the reference API. */
+int xrs_synth_terrain_f32(float *out, int64_t out_pitch, int64_t H, int64_t W,
+                          int64_t row0, int64_t col0, uint64_t seed, float zmin, float zmax,
+                          xrs_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XRS_B200_H */

@@ -1,0 +1,275 @@
+"""GPU parity: the CUDA path (called through the C ABI by the public API) vs the pinned CPU
+oracle and vs the committed reference outputs.  Runs on the B200 box (`-m gpu`)."""
+import numpy as np
+import pytest
+
+import oracle as o
+from helpers import assert_aspect_close, assert_close_f32, terrain
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+DEMS = ["smooth", "water", "nans", "integer", "rough", "tiny", "rand_2x4", "rand_10x15"]
+STATS = ["mean", "max", "min", "range", "std", "var", "sum"]
+
+
+@pytest.fixture(scope="module")
+def xb():
+    import xrspatial_b200
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    return xrspatial_b200
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def da(xb, data, res=(30.0, 30.0), name="r"):
+    return xb.DataArray(data, dims=("y", "x"), attrs={"res": res}, name=name)
+
+
+def host(x):
+    d = x.data
+    return d.cpu().numpy() if hasattr(d, "cpu") else np.asarray(d)
+
+
+def used_tma(xb):
+    return xb._lib.lib().xrs_debug_last_used_tma()
+
+
+# ----------------------------------------------------------------- committed reference outputs
+@pytest.mark.parametrize("case", DEMS)
+def test_surface_vs_reference_outputs(xb, refout, case):
+    z = refout["dem." + case]
+    agg = da(xb, dev(z))
+    assert_close_f32(host(xb.slope(agg)), refout["slope." + case], what="slope " + case)
+    assert_close_f32(host(xb.slope(da(xb, dev(z), res=(10.0, 25.5)))), refout["slope_aniso." + case],
+                     what="slope aniso " + case)
+    assert_aspect_close(host(xb.aspect(agg)), refout["aspect." + case], what=case)
+    ref = refout["curvature." + case]
+    assert_close_f32(host(xb.curvature(agg)), ref, atol=1e-6 * max(1.0, np.nanmax(np.abs(ref)) if np.isfinite(ref).any() else 1.0),
+                     what="curvature " + case)
+    assert_close_f32(host(xb.hillshade(agg)), refout["hillshade." + case], what="hillshade " + case)
+    assert_close_f32(host(xb.hillshade(agg, azimuth=315, angle_altitude=45)),
+                     refout["hillshade_az315_alt45." + case], what="hillshade2 " + case)
+
+
+@pytest.mark.parametrize("case", DEMS)
+def test_focal_mean_vs_reference_outputs(xb, refout, case):
+    z = refout["dem." + case]
+    # device f32 path (values = oracle rounded to f32), device f64 path (1e-12), host path (f64)
+    assert_close_f32(host(xb.mean(da(xb, dev(z)))), refout["focal_mean." + case], atol=0, what="mean f32")
+    out64 = host(xb.mean(da(xb, dev(z.astype(np.float64)))))
+    assert out64.dtype == np.float64
+    np.testing.assert_allclose(out64, refout["focal_mean." + case], rtol=1e-12, atol=0, equal_nan=True)
+    out3 = host(xb.mean(da(xb, dev(z.astype(np.float64))), passes=3))
+    np.testing.assert_allclose(out3, refout["focal_mean_p3." + case], rtol=1e-12, atol=0, equal_nan=True)
+    oute = host(xb.mean(da(xb, dev(z.astype(np.float64))), excludes=[np.nan, 0.0]))
+    np.testing.assert_allclose(oute, refout["focal_mean_ex." + case], rtol=1e-12, atol=0, equal_nan=True)
+    outh = xb.mean(da(xb, z)).data  # numpy in -> numpy float64 out
+    assert isinstance(outh, np.ndarray) and outh.dtype == np.float64
+    np.testing.assert_allclose(outh, refout["focal_mean." + case], rtol=1e-12, atol=0, equal_nan=True)
+
+
+@pytest.mark.parametrize("kn", ["box3", "box9", "mixed5", "mixed3x7", "mixed25", "int3"])
+def test_convolve_vs_reference_outputs(xb, refout, kn):
+    from xrspatial_b200.convolution import convolve_2d
+    k = refout["conv.kernel." + kn]
+    for key, okey in (("conv.dem", "conv.out." + kn), ("conv.dem_nan", "conv.out_nan." + kn)):
+        ref = refout[okey]
+        scale = np.nanmax(np.abs(ref[np.isfinite(ref)])) if np.isfinite(ref).any() else 1.0
+        got = convolve_2d(dev(refout[key]), k).cpu().numpy()
+        assert_close_f32(got, ref, atol=1e-6 * scale, what="conv " + kn)
+
+
+@pytest.mark.parametrize("mn", ["circle3", "full3", "annulus5", "rect3x5", "weights3"])
+def test_focal_stats_vs_reference_outputs(xb, refout, mn):
+    from xrspatial_b200 import focal
+    agg = da(xb, dev(refout["apply.dem"]))
+    res = focal.focal_stats(agg, refout["apply.mask." + mn], stats_funcs=STATS)
+    assert res.dims[0] == "stats" and tuple(res.shape) == (7,) + refout["apply.dem"].shape
+    got = host(res)
+    for i, s in enumerate(STATS):
+        ref = refout["apply.out.%s.%s" % (mn, s)]
+        atol = 1e-6 * np.nanmax(np.abs(ref)) if s in ("var",) else 1e-6
+        assert_close_f32(got[i], ref, atol=atol, what="%s %s" % (mn, s))
+
+
+def test_multispectral_vs_reference_outputs(xb, refout):
+    r = refout
+    b = {k: da(xb, dev(r["ms." + k])) for k in ("nir", "red", "blue", "green", "swir", "tir")}
+    eq = lambda got, key: np.testing.assert_array_equal(host(got), r[key], err_msg=key)  # noqa: E731
+    eq(xb.ndvi(b["nir"], b["red"]), "ms.ndvi")
+    eq(xb.savi(b["nir"], b["red"]), "ms.savi")
+    eq(xb.savi(b["nir"], b["red"], soil_factor=0.5), "ms.savi_L05")
+    eq(xb.evi(b["nir"], b["red"], b["blue"]), "ms.evi")
+    eq(xb.arvi(b["nir"], b["red"], b["blue"]), "ms.arvi")
+    eq(xb.gci(b["nir"], b["green"]), "ms.gci")
+    eq(xb.sipi(b["nir"], b["red"], b["blue"]), "ms.sipi")
+    eq(xb.ebbi(b["red"], b["swir"], b["tir"]), "ms.ebbi")
+    # host (numpy) path returns numpy
+    out = xb.ndvi(da(xb, r["ms.nir"]), da(xb, r["ms.red"])).data
+    assert isinstance(out, np.ndarray)
+    np.testing.assert_array_equal(out, r["ms.ndvi"])
+
+
+def check_zonal(df, ref, prefix, cols, rtol):
+    np.testing.assert_array_equal(np.asarray(df["zone"], dtype=np.float64), ref[prefix + "zone"].astype(np.float64))
+    for c in cols:
+        got, exp = np.asarray(df[c], dtype=np.float64), ref[prefix + c]
+        if c in ("count", "min", "max"):
+            np.testing.assert_array_equal(got, exp, err_msg=c)  # bit-exact
+        else:
+            np.testing.assert_allclose(got, exp, rtol=rtol, atol=rtol * np.nanmax(np.abs(exp)), equal_nan=True,
+                                       err_msg=c)
+
+
+def test_zonal_vs_reference_outputs(xb, refout):
+    r = refout
+    cols = ["mean", "max", "min", "sum", "std", "var", "count"]
+    zones, values = da(xb, dev(r["zonal.zones_i32"])), da(xb, dev(r["zonal.values_f32"]))
+    df = xb.zonal_stats(zones, values)
+    check_zonal(df, r, "zonal.f32_i32.", cols, 1e-5)
+    df = xb.zonal_stats(zones, values, zone_ids=[3, 7, 100, 999], nodata_values=0.0)
+    check_zonal(df, r, "zonal.f32_i32_ids_nodata.", cols, 1e-5)
+    df = xb.zonal_stats(da(xb, dev(r["zonal.zones_f64"])), da(xb, dev(r["zonal.values_f64"])))
+    check_zonal(df, r, "zonal.f64_f64.", cols, 1e-12)
+    arr = xb.zonal_stats(zones, values, zone_ids=[3, 7], stats_funcs=["mean", "count"],
+                         return_type="xarray.DataArray")
+    np.testing.assert_allclose(host(arr), r["zonal.f32_i32.broadcast_mean_count_3_7"], rtol=1e-5, equal_nan=True)
+    # host path
+    dfh = xb.zonal_stats(da(xb, r["zonal.zones_i32"]), da(xb, r["zonal.values_f32"]))
+    check_zonal(dfh, r, "zonal.f32_i32.", cols, 1e-5)
+    assert dfh["zone"].dtype == np.int32
+
+
+# ----------------------------------------------------------------- TMA path vs the oracle
+@pytest.mark.parametrize("shape,kw", [((300, 512), {}), ((517, 1024), dict(nans=0.01)),
+                                      ((1030, 260), dict(water=True)), ((64, 128), {}),
+                                      ((2048, 2048), {})])
+def test_tma_path_vs_oracle(xb, shape, kw):
+    rng = np.random.default_rng(hash(shape) % 1000)
+    z = terrain(rng, *shape, **kw)
+    agg = da(xb, dev(z))
+    s = host(xb.slope(agg))
+    assert used_tma(xb) == 1
+    assert_close_f32(s, o.slope(z, 30.0, 30.0, nthreads=8), what="slope")
+    assert_aspect_close(host(xb.aspect(agg)), o.aspect(z, nthreads=8))
+    ref = o.curvature(z, 30.0, nthreads=8)
+    assert_close_f32(host(xb.curvature(agg)), ref, atol=1e-6 * np.nanmax(np.abs(ref)), what="curvature")
+    assert_close_f32(host(xb.hillshade(agg)), o.hillshade(z, nthreads=8), what="hillshade")
+    assert_close_f32(host(xb.mean(agg)), o.focal_mean(z, nthreads=8), atol=0, what="focal mean")
+    assert used_tma(xb) == 1
+    out64 = host(xb.mean(da(xb, dev(z.astype(np.float64))), passes=2))
+    np.testing.assert_allclose(out64, o.focal_mean(z, passes=2, nthreads=8), rtol=1e-12, equal_nan=True)
+    # fused suite == individual kernels, bit for bit
+    suite = xb.surface_suite(agg)
+    np.testing.assert_array_equal(host(suite["slope"]), s)
+    np.testing.assert_array_equal(host(suite["aspect"]), host(xb.aspect(agg)))
+    np.testing.assert_array_equal(host(suite["curvature"]), host(xb.curvature(agg)))
+    np.testing.assert_array_equal(host(suite["hillshade"]), host(xb.hillshade(agg)))
+
+
+def test_tma_and_direct_kernels_agree_bitwise(xb):
+    """Same operator code behind both loaders: a W%4==0 raster (TMA) and the same raster seen
+    through a 1-column-shifted, non-16-byte-aligned view (direct loads) give identical cells."""
+    rng = np.random.default_rng(5)
+    z = terrain(rng, 200, 257, nans=0.02)
+    big = dev(z)
+    view = big[:, 1:]               # 256 wide, base pointer offset by 4 bytes -> direct kernel
+    a = xb.slope(da(xb, view))
+    assert used_tma(xb) == 0
+    b = xb.slope(da(xb, view.contiguous()))
+    assert used_tma(xb) == 1
+    np.testing.assert_array_equal(host(a), host(b))
+
+
+def test_host_path_matches_device_path(xb):
+    rng = np.random.default_rng(11)
+    z = terrain(rng, 700, 640, nans=0.01)
+    for fn in (xb.slope, xb.aspect, xb.curvature, xb.hillshade):
+        h = fn(da(xb, z)).data
+        d = fn(da(xb, dev(z))).data
+        assert isinstance(h, np.ndarray) and h.dtype == np.float32
+        np.testing.assert_array_equal(h, d.cpu().numpy(), err_msg=fn.__name__)
+    assert not np.shares_memory(z, h)
+
+
+def test_host_path_chunked_rows_invariant(xb):
+    """The host engine stripes rows in chunks with halos; force many chunks with a wide raster
+    and check against the oracle (partition invariance)."""
+    rng = np.random.default_rng(12)
+    z = terrain(rng, 300, 32768 * 2)
+    out = xb.slope(da(xb, z)).data      # 256 KiB rows -> 128 rows per chunk -> 3 chunks
+    assert_close_f32(out, o.slope(z, 30.0, 30.0, nthreads=8), what="chunked slope")
+    from xrspatial_b200.convolution import convolve_2d
+    k = np.ones((9, 9)) / 81.0
+    got = convolve_2d(z[:, :4096].copy(), k)
+    ref = o.convolve_2d(z[:, :4096], k, nthreads=8)
+    assert_close_f32(got, ref, atol=1e-6 * np.nanmax(np.abs(ref)), what="host convolve")
+
+
+@pytest.mark.parametrize("k", [3, 9, 25])
+def test_convolve_sizes_vs_oracle(xb, k):
+    from xrspatial_b200.convolution import convolve_2d
+    rng = np.random.default_rng(k)
+    z = terrain(rng, 260, 384, nans=0.001)
+    for kern in (np.ones((k, k)) / (k * k), rng.standard_normal((k, k))):
+        ref = o.convolve_2d(z, kern, nthreads=8)
+        got = convolve_2d(dev(z), kern).cpu().numpy()
+        assert_close_f32(got, ref, atol=1e-6 * np.nanmax(np.abs(ref[np.isfinite(ref)])), what="conv k=%d" % k)
+
+
+def test_focal_stats_tma_vs_oracle(xb):
+    from xrspatial_b200 import focal
+    from xrspatial_b200.convolution import circle_kernel
+    rng = np.random.default_rng(3)
+    z = terrain(rng, 130, 256, nans=0.03)
+    kern = circle_kernel(1, 1, 3)
+    res = host(focal.focal_stats(da(xb, dev(z)), kern, stats_funcs=STATS))
+    for i, s in enumerate(STATS):
+        ref = o.focal_apply(z, kern, s, nthreads=8)
+        atol = 1e-6 * np.nanmax(np.abs(ref)) if s == "var" else 1e-6
+        assert_close_f32(res[i], ref, atol=atol, what=s)
+
+
+def test_input_not_modified_and_metadata(xb):
+    rng = np.random.default_rng(1)
+    z = terrain(rng, 40, 64)
+    t = dev(z)
+    agg = xb.DataArray(t, dims=("y", "x"), coords={"y": np.arange(40)[::-1], "x": np.arange(64)},
+                       attrs={"res": (1, 1), "crs": "x"}, name="dem")
+    out = xb.slope(agg, name="myslope")
+    assert out.name == "myslope" and out.dims == agg.dims and out.attrs == agg.attrs
+    assert type(out.data) is type(t) and tuple(out.shape) == z.shape and out.data.dtype == torch.float32
+    np.testing.assert_array_equal(t.cpu().numpy(), z)
+
+
+def test_empty_and_degenerate_rasters(xb):
+    for shape in ((0, 0), (1, 1), (1, 7), (5, 1), (2, 2)):
+        z = np.arange(shape[0] * shape[1], dtype=np.float32).reshape(shape)
+        out = host(xb.slope(da(xb, dev(z))))
+        assert out.shape == shape and np.isnan(out).all()
+        m = host(xb.mean(da(xb, dev(z))))
+        assert m.shape == shape
+        if z.size:
+            assert_close_f32(m, o.focal_mean(z), atol=0)
+
+
+def test_large_zonal_blocks_and_scatter(xb):
+    """1024 zones as a 32x32 block grid and as a scattered hash (SURVEY.md 8d zones)."""
+    rng = np.random.default_rng(7)
+    H = W = 1024
+    values = terrain(rng, H, W, nans=0.001)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for zones in (((yy // 32) * 32 + xx // 32).astype(np.int32),
+                  ((yy * 7919 + xx * 104729) % 1024).astype(np.int32)):
+        df = xb.zonal_stats(da(xb, dev(zones)), da(xb, dev(values)))
+        ref = o.zonal_stats(zones, values)
+        np.testing.assert_array_equal(np.asarray(df["zone"]), ref["zone"])
+        np.testing.assert_array_equal(np.asarray(df["count"]), ref["count"])
+        np.testing.assert_array_equal(np.asarray(df["min"]), ref["min"])
+        np.testing.assert_array_equal(np.asarray(df["max"]), ref["max"])
+        for c in ("mean", "sum", "std", "var"):
+            np.testing.assert_allclose(np.asarray(df[c]), ref[c], rtol=1e-5, err_msg=c)

@@ -1,0 +1,26 @@
+"""xrspatial.aspect on the B200 backend (reference: aspect.py:274-388, planar)."""
+from ._xr import DataArray
+from .dataset_support import supports_dataset
+from .utils import ArrayTypeFunctionMapping, run_stencil_device, run_stencil_host
+
+
+def _run_numpy(data):
+    """replaces aspect.py:56 `_run_numpy`."""
+    return run_stencil_host("aspect", data)
+
+
+def _run_cupy(data):
+    """replaces aspect.py:139 `_run_cupy`; follows the CPU path (no 359.999 clamp)."""
+    return run_stencil_device("xrs_aspect_f32", data)
+
+
+@supports_dataset
+def aspect(agg, name='aspect', method='planar', z_unit='meter'):
+    """Compass aspect in degrees, -1 on flats, NaN ring (float32)."""
+    if method not in ('planar', 'geodesic'):
+        raise ValueError(f"method must be 'planar' or 'geodesic', got {method!r}")
+    if method == 'geodesic':
+        raise NotImplementedError("method='geodesic' is not part of the B200 stencil hot path")
+    mapper = ArrayTypeFunctionMapping(numpy_func=_run_numpy, cupy_func=_run_cupy)
+    out = mapper(agg)(agg.data)
+    return DataArray(out, name=name, coords=agg.coords, dims=agg.dims, attrs=agg.attrs)

@@ -1,0 +1,350 @@
+// conv.cu -- general k x k neighbourhood operators: convolve_2d (convolution.py:285-313) and
+// the masked focal statistics behind focal.apply / focal_stats (focal.py:305-326, 268-302).
+//
+// One CTA (256 threads = 32 x 8) per 128 x 32 output tile, persistent over tiles.  The
+// (tile + halo) block is brought into shared memory by TMA 2-D bulk loads with NaN
+// out-of-bounds fill: for convolve_2d that produces the reference's NaN ring for free
+// (NaN * w = NaN, even for w = 0), for the focal statistics out-of-raster cells are skipped
+// exactly like NaN cells, which is the reference's clamped window.
+//
+// convolve_2d: the tile is widened to float64 once in shared memory; every thread owns a
+// 4 x 4 block of outputs and accumulates in float64 with FMA (the reference accumulates
+// `kernel(f64) * data(f32)` in a float64 `num`); weights are read from the kernel-parameter
+// constant bank.  Bound: FP64 FMA rate for k >= 5 (2*k*k flop/cell), HBM for k = 3.
+#include "common.cuh"
+
+namespace xrs {
+
+constexpr int kMaxTaps = 2401;  // up to 49 x 49
+constexpr int kTileW = 128, kTileH = 32;
+
+struct ConvWeights {
+    double w[kMaxTaps];
+};
+struct MaskBits {
+    unsigned char m[kMaxTaps];
+};
+
+struct TileGeom {
+    int64_t H, W;
+    int kh, kw, ry, rx;
+    int sw;        // shared tile width (cells), multiple of 4
+    int sh;        // shared tile height = kTileH + kh - 1
+    int tiles_x, tiles_y;
+    int box_h;     // rows per TMA box (sh is loaded in ceil(sh / box_h) boxes)
+};
+
+__device__ __forceinline__ void load_tile_tma(const CUtensorMap *tmap, float *tile32, uint64_t *bar,
+                                              const TileGeom &g, int tx0, int ty0, uint32_t parity) {
+    // one elected thread issues the boxes; everyone waits on the mbarrier
+    if (threadIdx.x == 0) {
+        const int nbox = (g.sh + g.box_h - 1) / g.box_h;
+        mbar_arrive_expect_tx(bar, (uint32_t)(nbox * g.box_h * g.sw * sizeof(float)));
+        for (int b = 0; b < nbox; ++b)
+            tma_load_2d(tile32 + (size_t)b * g.box_h * g.sw, tmap, bar, tx0 - g.rx, ty0 - g.ry + b * g.box_h);
+    }
+    mbar_wait(bar, parity);
+}
+
+// ----------------------------------------------------------------------------- convolve
+__global__ void __launch_bounds__(256)
+conv2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ConvWeights cw,
+              float *__restrict__ out, int64_t out_pitch_elems, const TileGeom g) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int nbox = (g.sh + g.box_h - 1) / g.box_h;
+    const size_t tile_cells = (size_t)nbox * g.box_h * g.sw;
+    // tile32 first: TMA destinations must be 128-byte aligned (box_h * sw * 4 is, see tile_geom)
+    float *tile32 = reinterpret_cast<float *>(smem_raw);
+    const size_t off64 = (tile_cells * sizeof(float) + 127) / 128 * 128;
+    double *tile64 = reinterpret_cast<double *>(smem_raw + off64);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + off64 + tile_cells * sizeof(double));
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap);
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t n_tiles = (int64_t)g.tiles_x * g.tiles_y;
+    uint32_t parity = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int tile_y = (int)(t / g.tiles_x), tile_x = (int)(t % g.tiles_x);
+        const int x0 = tile_x * kTileW, y0 = tile_y * kTileH;
+        load_tile_tma(&tmap, tile32, bar, g, x0, y0, parity);
+        parity ^= 1u;
+        // widen once: f32 -> f64
+        for (size_t i = threadIdx.x; i < (size_t)g.sh * g.sw; i += blockDim.x) tile64[i] = (double)tile32[i];
+        __syncthreads();
+
+        double acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+
+        const int rows_in = 4 + g.kh - 1;
+        for (int j = 0; j < rows_in; ++j) {
+            const double *rowp = tile64 + (size_t)(ty * 4 + j) * g.sw + 4 * tx;
+            for (int kb = 0; kb < g.kw; kb += 4) {
+                double v[8];
+                const double2 q0 = *reinterpret_cast<const double2 *>(rowp + kb);
+                const double2 q1 = *reinterpret_cast<const double2 *>(rowp + kb + 2);
+                const double2 q2 = *reinterpret_cast<const double2 *>(rowp + kb + 4);
+                const double2 q3 = *reinterpret_cast<const double2 *>(rowp + kb + 6);
+                v[0] = q0.x; v[1] = q0.y; v[2] = q1.x; v[3] = q1.y;
+                v[4] = q2.x; v[5] = q2.y; v[6] = q3.x; v[7] = q3.y;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int ky = j - r;
+                    if (ky >= 0 && ky < g.kh) {
+#pragma unroll
+                        for (int tt = 0; tt < 4; ++tt) {
+                            if (kb + tt < g.kw) {
+                                const double wv = cw.w[ky * g.kw + kb + tt];
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) acc[r][c] = fma(wv, v[c + tt], acc[r][c]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        const int64_t xo = (int64_t)x0 + 4 * tx;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int64_t yo = (int64_t)y0 + ty * 4 + r;
+            if (yo < g.H && xo < g.W)  // W % 4 == 0 on this path
+                __stcs(reinterpret_cast<float4 *>(out + yo * out_pitch_elems + xo),
+                       make_float4((float)acc[r][0], (float)acc[r][1], (float)acc[r][2], (float)acc[r][3]));
+        }
+        __syncthreads();  // tile buffers are reused by the next iteration
+    }
+}
+
+// Fallback for rasters TMA cannot describe: one thread per cell, bounds-checked loads.
+__global__ void __launch_bounds__(256)
+conv2d_direct_kernel(const float *__restrict__ in, int64_t in_pitch_elems, const __grid_constant__ ConvWeights cw,
+                     float *__restrict__ out, int64_t out_pitch_elems, int64_t H, int64_t W, int kh, int kw) {
+    const int64_t n = H * W;
+    const int ry = kh / 2, rx = kw / 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t y = i / W, x = i % W;
+        double acc = 0.0;
+        for (int ky = 0; ky < kh; ++ky)
+            for (int kx = 0; kx < kw; ++kx) {
+                const int64_t yy = y + ky - ry, xx = x + kx - rx;
+                const double v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? (double)in[yy * in_pitch_elems + xx]
+                                                                            : nan_of<double>();
+                acc = fma(cw.w[ky * kw + kx], v, acc);
+            }
+        out[y * out_pitch_elems + x] = (float)acc;
+    }
+}
+
+// ----------------------------------------------------------------------------- focal statistics
+// Reducers follow Numba's nan-functions (numba/np/arraymath.py) as used by focal.py:268-302:
+// mean/var/std accumulate in f64 (var two-pass about the f64 mean), sum accumulates in f32 in
+// row-major window order (bit-identical to np.nansum on the f32 scratch), min/max skip NaN.
+template <typename Fetch>
+__device__ __forceinline__ float focal_reduce(const Fetch &fetch, const MaskBits &mask, int kh, int kw, int stat) {
+    if (stat == XRS_STAT_MEAN || stat == XRS_STAT_VAR || stat == XRS_STAT_STD) {
+        double c = 0.0;
+        int cnt = 0;
+        for (int ky = 0; ky < kh; ++ky)
+            for (int kx = 0; kx < kw; ++kx)
+                if (mask.m[ky * kw + kx]) {
+                    const float v = fetch(ky, kx);
+                    if (v == v) { c += (double)v; ++cnt; }
+                }
+        const double m = c / (double)cnt;
+        if (stat == XRS_STAT_MEAN) return (float)m;
+        double ssd = 0.0;
+        for (int ky = 0; ky < kh; ++ky)
+            for (int kx = 0; kx < kw; ++kx)
+                if (mask.m[ky * kw + kx]) {
+                    const float v = fetch(ky, kx);
+                    if (v == v) { const double d = (double)v - m; ssd += d * d; }
+                }
+        const double var = ssd / (double)cnt;
+        return (float)(stat == XRS_STAT_VAR ? var : sqrt(var));
+    } else if (stat == XRS_STAT_SUM) {
+        float c = 0.f;
+        for (int ky = 0; ky < kh; ++ky)
+            for (int kx = 0; kx < kw; ++kx)
+                if (mask.m[ky * kw + kx]) {
+                    const float v = fetch(ky, kx);
+                    if (v == v) c += v;
+                }
+        return c;
+    } else {
+        // nanmin / nanmax start from scratch[0] (NaN unless the first window cell takes part)
+        float mn = nan_of<float>(), mx = nan_of<float>();
+        for (int ky = 0; ky < kh; ++ky)
+            for (int kx = 0; kx < kw; ++kx)
+                if (mask.m[ky * kw + kx]) {
+                    const float v = fetch(ky, kx);
+                    if (v == v) {
+                        if (!(mn < v)) mn = v;
+                        if (!(mx > v)) mx = v;
+                    }
+                }
+        return stat == XRS_STAT_MIN ? mn : stat == XRS_STAT_MAX ? mx : mx - mn;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+focal_stat_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MaskBits mask,
+                  float *__restrict__ out, int64_t out_pitch_elems, const TileGeom g, int stat) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int nbox = (g.sh + g.box_h - 1) / g.box_h;
+    const size_t tile_cells = (size_t)nbox * g.box_h * g.sw;
+    float *tile32 = reinterpret_cast<float *>(smem_raw);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + tile_cells * sizeof(float));
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap);
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int64_t n_tiles = (int64_t)g.tiles_x * g.tiles_y;
+    uint32_t parity = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int tile_y = (int)(t / g.tiles_x), tile_x = (int)(t % g.tiles_x);
+        const int x0 = tile_x * kTileW, y0 = tile_y * kTileH;
+        load_tile_tma(&tmap, tile32, bar, g, x0, y0, parity);
+        parity ^= 1u;
+        for (int o = threadIdx.x; o < kTileW * kTileH; o += blockDim.x) {
+            const int lx = o % kTileW, ly = o / kTileW;
+            const int64_t xo = (int64_t)x0 + lx, yo = (int64_t)y0 + ly;
+            if (xo < g.W && yo < g.H) {
+                const float *base = tile32 + (size_t)ly * g.sw + lx;
+                const int sw = g.sw;
+                auto fetch = [base, sw](int ky, int kx) { return base[ky * sw + kx]; };
+                out[yo * out_pitch_elems + xo] = focal_reduce(fetch, mask, g.kh, g.kw, stat);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+focal_stat_direct_kernel(const float *__restrict__ in, int64_t in_pitch_elems, const __grid_constant__ MaskBits mask,
+                         float *__restrict__ out, int64_t out_pitch_elems, int64_t H, int64_t W, int kh, int kw,
+                         int stat) {
+    const int64_t n = H * W;
+    const int ry = kh / 2, rx = kw / 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t y = i / W, x = i % W;
+        auto fetch = [=](int ky, int kx) {
+            const int64_t yy = y + ky - ry, xx = x + kx - rx;
+            return (yy >= 0 && yy < H && xx >= 0 && xx < W) ? in[yy * in_pitch_elems + xx] : nan_of<float>();
+        };
+        out[y * out_pitch_elems + x] = focal_reduce(fetch, mask, kh, kw, stat);
+    }
+}
+
+static int check_common(const float *in, int64_t in_pitch, float *out, int64_t out_pitch, int64_t H, int64_t W,
+                        const double *kernel, int kh, int kw) {
+    XRS_REQUIRE(in && out && kernel, "NULL pointer");
+    XRS_REQUIRE((const void *)in != (const void *)out, "in and out must not alias");
+    XRS_REQUIRE(kh >= 1 && kw >= 1 && (kh & 1) && (kw & 1), "kernel dimensions must be odd");
+    XRS_REQUIRE(kh * kw <= kMaxTaps && kh <= 63 && kw <= 63, "kernel too large (max 49x49 taps, 63 per side)");
+    XRS_REQUIRE(in_pitch % 4 == 0 && in_pitch >= W * 4 && out_pitch % 4 == 0 && out_pitch >= W * 4,
+                "pitches must be multiples of 4 bytes and >= row bytes");
+    XRS_REQUIRE(H < (1LL << 31) - 64 && W < (1LL << 31) - 256, "raster dimension too large");
+    return XRS_OK;
+}
+
+static bool tile_geom(TileGeom &g, CUtensorMap *tmap, const float *in, int64_t in_pitch, float *out,
+                      int64_t out_pitch, int64_t H, int64_t W, int kh, int kw) {
+    g.H = H; g.W = W; g.kh = kh; g.kw = kw; g.ry = kh / 2; g.rx = kw / 2;
+    // the 8-wide chunk loads of the convolution reach 4*31 + 4*((kw-1)/4) + 7 cells into a row
+    g.sw = ((kTileW + ((kw + 3) / 4) * 4 + 4) + 3) / 4 * 4;
+    g.sh = kTileH + kh - 1;
+    g.tiles_x = (int)((W + kTileW - 1) / kTileW);
+    g.tiles_y = (int)((H + kTileH - 1) / kTileH);
+    g.box_h = g.sh <= 64 ? g.sh : 48;  // 48 % 8 == 0 keeps the 2nd box 128-byte aligned
+    if (g.sw > 256) return false;
+    if (W % 4 != 0 || out_pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(out) & 15)) return false;
+    return make_tensor_map_2d(tmap, in, in_pitch, H, W, 4, g.sw, g.box_h);
+}
+
+}  // namespace xrs
+
+using namespace xrs;
+
+extern "C" {
+
+int xrs_convolve2d_f32(const float *in, int64_t in_pitch, float *out, int64_t out_pitch, int64_t H, int64_t W,
+                       const double *kernel, int kh, int kw, xrs_stream_t s) {
+    if (H <= 0 || W <= 0) return XRS_OK;
+    const int rc = check_common(in, in_pitch, out, out_pitch, H, W, kernel, kh, kw);
+    if (rc) return rc;
+    static thread_local ConvWeights cw;
+    for (int i = 0; i < kh * kw; ++i) cw.w[i] = kernel[i];
+    TileGeom g;
+    CUtensorMap tmap;
+    const int sms = sm_count();
+    if (tile_geom(g, &tmap, in, in_pitch, out, out_pitch, H, W, kh, kw)) {
+        const int nbox = (g.sh + g.box_h - 1) / g.box_h;
+        const size_t cells = (size_t)nbox * g.box_h * g.sw;
+        const size_t smem = (cells * 4 + 127) / 128 * 128 + cells * 8 + 16;
+        if (smem <= 227 * 1024) {
+            XRS_CUDA(cudaFuncSetAttribute(conv2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = (int)((227 * 1024) / (smem + 1024));
+            if (per_sm > 4) per_sm = 4;
+            if (per_sm < 1) per_sm = 1;
+            int64_t grid = (int64_t)sms * per_sm;
+            const int64_t n_tiles = (int64_t)g.tiles_x * g.tiles_y;
+            if (grid > n_tiles) grid = n_tiles;
+            conv2d_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)s>>>(tmap, cw, out, out_pitch / 4, g);
+            XRS_CUDA(cudaGetLastError());
+            return XRS_OK;
+        }
+    }
+    int64_t grid = (H * W + 255) / 256;
+    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
+    conv2d_direct_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)s>>>(in, in_pitch / 4, cw, out, out_pitch / 4, H, W,
+                                                                     kh, kw);
+    XRS_CUDA(cudaGetLastError());
+    return XRS_OK;
+}
+
+int xrs_focal_stat_f32(const float *in, int64_t in_pitch, float *out, int64_t out_pitch, int64_t H, int64_t W,
+                       const double *kernel, int kh, int kw, int stat, xrs_stream_t s) {
+    if (H <= 0 || W <= 0) return XRS_OK;
+    const int rc = check_common(in, in_pitch, out, out_pitch, H, W, kernel, kh, kw);
+    if (rc) return rc;
+    XRS_REQUIRE(stat >= XRS_STAT_MEAN && stat <= XRS_STAT_VAR, "unknown focal statistic");
+    static thread_local MaskBits mask;
+    for (int i = 0; i < kh * kw; ++i) mask.m[i] = (kernel[i] == 1.0) ? 1 : 0;  // focal.py:323
+    TileGeom g;
+    CUtensorMap tmap;
+    const int sms = sm_count();
+    if (tile_geom(g, &tmap, in, in_pitch, out, out_pitch, H, W, kh, kw)) {
+        const int nbox = (g.sh + g.box_h - 1) / g.box_h;
+        const size_t smem = (size_t)nbox * g.box_h * g.sw * 4 + 16;
+        if (smem <= 227 * 1024) {
+            XRS_CUDA(cudaFuncSetAttribute(focal_stat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = (int)((227 * 1024) / (smem + 1024));
+            if (per_sm > 4) per_sm = 4;
+            if (per_sm < 1) per_sm = 1;
+            int64_t grid = (int64_t)sms * per_sm;
+            const int64_t n_tiles = (int64_t)g.tiles_x * g.tiles_y;
+            if (grid > n_tiles) grid = n_tiles;
+            focal_stat_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)s>>>(tmap, mask, out, out_pitch / 4, g, stat);
+            XRS_CUDA(cudaGetLastError());
+            return XRS_OK;
+        }
+    }
+    int64_t grid = (H * W + 255) / 256;
+    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
+    focal_stat_direct_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)s>>>(in, in_pitch / 4, mask, out, out_pitch / 4,
+                                                                         H, W, kh, kw, stat);
+    XRS_CUDA(cudaGetLastError());
+    return XRS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,291 @@
+// surface_ops.cuh -- per-row operators for the 3x3 skeleton (stencil3.cuh).
+//
+// Numerics follow the reference's *CPU* kernels, which do the Horn sums in float64 because
+// Numba promotes `2 * f32`: the column differences / weighted row
+// sums are formed in f64 (they are EXACT there for any realistic raster: sums of <= 8
+// float32 values), so re-associating them row by row changes nothing; the transcendental
+// tail (sqrt / atan / atan2) is evaluated in f32 on the correctly-rounded f64 intermediate,
+// which keeps the result within ~3e-7 relative of the oracle (bar: 1e-5).
+#pragma once
+#include "stencil3.cuh"
+
+namespace xrs {
+
+// Column difference D[i] = right - left and Horn row sum S[i] = left + 2*mid + right of one
+// input row, in f64, for the 4 cells of a lane.
+struct HornRow {
+    double D[4], S[4];
+};
+__device__ __forceinline__ HornRow horn_row(const Row6<float> &r) {
+    double w[6];
+    w[0] = (double)r.l;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i + 1] = (double)r.c[i];
+    w[5] = (double)r.r;
+    HornRow h;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        h.D[i] = w[i + 2] - w[i];
+        h.S[i] = fma(2.0, w[i + 1], w[i]) + w[i + 2];
+    }
+    return h;
+}
+
+// ------------------------------------------------------------------ slope (slope.py:56-76)
+struct SlopeOp {
+    using in_t = float;
+    using out_t = float;
+    static constexpr int kOutputs = 1;
+    struct Params {
+        double kx, ky;  // 1/(8*cellsize_x), 1/(8*cellsize_y)
+    };
+    const Params &p;
+    HornRow m2, m1;  // rows y-2, y-1 relative to the row being pushed
+    __device__ explicit SlopeOp(const Params &pp) : p(pp) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) m2.D[i] = m2.S[i] = m1.D[i] = m1.S[i] = 0.0;
+    }
+    static __device__ __forceinline__ float eval(double X, double Y, const Params &p) {
+        const double dx = X * p.kx, dy = Y * p.ky;
+        const float pf = (float)fma(dx, dx, dy * dy);
+        return atan_sqrt_deg(pf);
+    }
+    __device__ __forceinline__ void step(const Row6<float> &row, Vec4<float> (&out)[1]) {
+        const HornRow n = horn_row(row);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            // dz_dx*8cs = (c+2f+i)-(a+2d+g) = D(y+1)+2D(y)+D(y-1);  dz_dy*8cs = S(y-1)-S(y+1)
+            const double X = fma(2.0, m1.D[i], m2.D[i]) + n.D[i];
+            const double Y = m2.S[i] - n.S[i];
+            out[0].v[i] = eval(X, Y, p);
+        }
+        m2 = m1;
+        m1 = n;
+    }
+};
+
+// ------------------------------------------------------------------ aspect (aspect.py:56-90)
+struct AspectOp {
+    using in_t = float;
+    using out_t = float;
+    static constexpr int kOutputs = 1;
+    struct Params {
+        int unused;
+    };
+    HornRow m2, m1;
+    __device__ explicit AspectOp(const Params &) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) m2.D[i] = m2.S[i] = m1.D[i] = m1.S[i] = 0.0;
+    }
+    // X = 8*dz_dx, Y = 8*dz_dy (exact).  compass = (90 - atan2(Y, -X)) mod 360, which is
+    // atan2(-X, Y) folded into [0, 360): evaluating it directly keeps full relative
+    // accuracy near 0 degrees, where `90 - theta` would cancel.
+    static __device__ __forceinline__ float eval(double X, double Y) {
+        if (X == 0.0 && Y == 0.0) return -1.0f;
+        const float a = atan2_deg((float)(-X), (float)Y);
+        return a < 0.0f ? a + 360.0f : a;
+    }
+    __device__ __forceinline__ void step(const Row6<float> &row, Vec4<float> (&out)[1]) {
+        const HornRow n = horn_row(row);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double X = fma(2.0, m1.D[i], m2.D[i]) + n.D[i];
+            const double Y = n.S[i] - m2.S[i];  // a,b,c = row y-1 here (aspect.py:65-72)
+            out[0].v[i] = eval(X, Y);
+        }
+        m2 = m1;
+        m1 = n;
+    }
+};
+
+// ------------------------------------------------------------------ curvature (curvature.py:31-41)
+// The reference forms N+S and E+W in float32 (rounded) before promoting; reproduce that, then
+// 4C - ns - ew is exact in f64 and only the final scale rounds.
+struct CurvatureOp {
+    using in_t = float;
+    using out_t = float;
+    static constexpr int kOutputs = 1;
+    struct Params {
+        double k;  // 100 / cellsize^2
+    };
+    const Params &p;
+    float n2[4];      // row y-2 centre cells
+    Row6<float> r1;   // row y-1
+    __device__ explicit CurvatureOp(const Params &pp) : p(pp) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) n2[i] = 0.f, r1.c[i] = 0.f;
+        r1.l = r1.r = 0.f;
+    }
+    static __device__ __forceinline__ float eval(float ns, float ew, float c, double k) {
+        // -2*(d+e) with d = ns/2 - c, e = ew/2 - c  ==  4c - ns - ew
+        const double t = fma(4.0, (double)c, -(double)ns) - (double)ew;
+        return (float)(t * k);
+    }
+    __device__ __forceinline__ void step(const Row6<float> &row, Vec4<float> (&out)[1]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float ns = row.c[i] + n2[i];
+            const float e = (i == 3) ? r1.r : r1.c[i + 1];
+            const float w = (i == 0) ? r1.l : r1.c[i - 1];
+            out[0].v[i] = eval(ns, e + w, r1.c[i], p.k);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) n2[i] = r1.c[i];
+        r1 = row;
+    }
+};
+
+// ------------------------------------------------------------------ hillshade (hillshade.py:20-35)
+// With g = |grad|, slope = pi/2 - atan g and aspect = atan2(-gx, gy) the reference's
+//   sin(alt) sin(slope) + cos(alt) cos(slope) cos((az - pi/2) - aspect)
+// equals  [sin(alt) + cos(alt) (cosA gy - sinA gx)] / sqrt(1 + g^2),  A = az - pi/2,
+// so no trigonometric function is needed per cell (all float32, like the reference's
+// np.gradient / ufunc chain; agreement ~2e-7 absolute on values in [0, 1]).
+struct HillshadeOp {
+    using in_t = float;
+    using out_t = float;
+    static constexpr int kOutputs = 1;
+    struct Params {
+        float s0, cy, cx;  // sin(alt), 0.5*cos(alt)*cos(A), 0.5*cos(alt)*sin(A)
+    };
+    const Params &p;
+    float n2[4];
+    Row6<float> r1;
+    __device__ explicit HillshadeOp(const Params &pp) : p(pp) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) n2[i] = 0.f, r1.c[i] = 0.f;
+        r1.l = r1.r = 0.f;
+    }
+    static __device__ __forceinline__ float eval(float gx2, float gy2, const Params &p) {
+        // gx2 = 2*d/drow, gy2 = 2*d/dcol
+        const float q = fmaf(gx2, gx2, gy2 * gy2);
+        const float rinv = rsqrt_approx(fmaf(0.25f, q, 1.0f));
+        const float num = fmaf(p.cy, gy2, fmaf(-p.cx, gx2, p.s0));
+        return fmaf(0.5f * num, rinv, 0.5f);
+    }
+    __device__ __forceinline__ void step(const Row6<float> &row, Vec4<float> (&out)[1]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float e = (i == 3) ? r1.r : r1.c[i + 1];
+            const float w = (i == 0) ? r1.l : r1.c[i - 1];
+            out[0].v[i] = eval(row.c[i] - n2[i], e - w, p);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) n2[i] = r1.c[i];
+        r1 = row;
+    }
+};
+
+// ------------------------------------------------------------------ fused surface suite
+// analytics.summarize_terrain (analytics.py:84-86): slope + aspect + curvature (+ hillshade)
+// from ONE read of the DEM.  Output k is skipped when its pointer is NULL.
+struct SuiteOp {
+    using in_t = float;
+    using out_t = float;
+    static constexpr int kOutputs = 4;  // slope, aspect, curvature, hillshade
+    struct Params {
+        SlopeOp::Params slope;
+        CurvatureOp::Params curv;
+        HillshadeOp::Params hill;
+    };
+    const Params &p;
+    HornRow m2, m1;
+    float n2[4];
+    Row6<float> r1;
+    __device__ explicit SuiteOp(const Params &pp) : p(pp) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            m2.D[i] = m2.S[i] = m1.D[i] = m1.S[i] = 0.0;
+            n2[i] = 0.f;
+            r1.c[i] = 0.f;
+        }
+        r1.l = r1.r = 0.f;
+    }
+    __device__ __forceinline__ void step(const Row6<float> &row, Vec4<float> (&out)[4]) {
+        const HornRow n = horn_row(row);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double X = fma(2.0, m1.D[i], m2.D[i]) + n.D[i];
+            const double Ys = m2.S[i] - n.S[i];
+            out[0].v[i] = SlopeOp::eval(X, Ys, p.slope);
+            out[1].v[i] = AspectOp::eval(X, -Ys);
+            const float e = (i == 3) ? r1.r : r1.c[i + 1];
+            const float w = (i == 0) ? r1.l : r1.c[i - 1];
+            out[2].v[i] = CurvatureOp::eval(row.c[i] + n2[i], e + w, r1.c[i], p.curv.k);
+            out[3].v[i] = HillshadeOp::eval(row.c[i] - n2[i], e - w, p.hill);
+        }
+        m2 = m1;
+        m1 = n;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) n2[i] = r1.c[i];
+        r1 = row;
+    }
+};
+
+// sum / cnt for cnt in 0..9 without a f64 division: multiply by a tabulated reciprocal and
+// apply one FMA correction step (the quotient is then correctly rounded except in rare
+// halfway cases; 0/0 gives NaN like np.divide).
+__constant__ double kRcp9[10] = {
+    0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9};
+__device__ __forceinline__ double div_count9(double s, int cnt) {
+    if (cnt == 0) return nan_of<double>();
+    const double r = kRcp9[cnt], n = (double)cnt;
+    const double q = s * r;
+    const double e = fma(-q, n, s);
+    return fma(e, r, q);
+}
+
+// ------------------------------------------------------------------ focal.mean (focal.py:44-67)
+// 3x3 NaN-skipping mean over the window clamped to the raster (out-of-raster cells arrive
+// as NaN and are skipped like any NaN); centre cells matching `excludes` are copied.
+template <typename T> struct FocalMeanOp {
+    using in_t = T;
+    using out_t = T;
+    static constexpr int kOutputs = 1;
+    static constexpr int kMaxEx = 8;
+    struct Params {
+        double ex[kMaxEx];
+        int n_ex;
+        int ex_nan;  // some exclude is NaN
+    };
+    const Params &p;
+    double s2[4], s1[4];  // horizontal 3-sums of rows y-2, y-1 (NaN -> 0)
+    int c2[4], c1[4];     // matching counts
+    T ctr[4];             // centre cells of row y-1
+    __device__ explicit FocalMeanOp(const Params &pp) : p(pp) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s2[i] = s1[i] = 0.0, c2[i] = c1[i] = 0, ctr[i] = (T)0;
+    }
+    __device__ __forceinline__ void step(const Row6<T> &row, Vec4<T> (&out)[1]) {
+        double f[6];
+        int m[6];
+        T w[6];
+        w[0] = row.l; w[5] = row.r;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i + 1] = row.c[i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const bool ok = (w[i] == w[i]);
+            f[i] = ok ? (double)w[i] : 0.0;
+            m[i] = ok ? 1 : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double hs = (f[i] + f[i + 1]) + f[i + 2];
+            const int hc = m[i] + m[i + 1] + m[i + 2];
+            const double sum = (s2[i] + s1[i]) + hs;
+            const int cnt = c2[i] + c1[i] + hc;
+            const T c = ctr[i];
+            bool excl = (p.ex_nan != 0) && !(c == c);
+            for (int k = 0; k < p.n_ex; ++k) excl = excl || ((double)c == p.ex[k]);
+            const T mean = (T)div_count9(sum, cnt);
+            out[0].v[i] = excl ? c : mean;
+            s2[i] = s1[i]; s1[i] = hs;
+            c2[i] = c1[i]; c1[i] = hc;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ctr[i] = row.c[i];
+    }
+};
+
+}  // namespace xrs

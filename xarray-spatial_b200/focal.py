@@ -1,0 +1,150 @@
+"""xrspatial.focal on the B200 backend (reference: focal.py): mean, apply, focal_stats.
+
+`apply` accepts the built-in reducers only (`_calc_mean`, `_calc_sum`, ... or their names): an
+arbitrary Python/Numba callable cannot cross the C ABI.
+`hotspots` is outside the hot path.
+"""
+import ctypes
+
+import numpy as np
+import pandas as pd
+
+from . import _lib
+from ._xr import DataArray, concat
+from .convolution import custom_kernel
+from .dataset_support import supports_dataset
+from .utils import (ArrayTypeFunctionMapping, _dbl_array, as_device_tensor, is_device_array,
+                    like_container, run_stencil_device, run_stencil_host)
+
+
+class _Reducer(object):
+    """Named window reducer; stands in for the reference's @ngjit `_calc_*` functions."""
+
+    def __init__(self, stat):
+        self.stat = stat
+        self.__name__ = "_calc_" + stat
+
+    def __repr__(self):
+        return "<focal reducer %s>" % self.stat
+
+
+_calc_mean = _Reducer("mean")
+_calc_sum = _Reducer("sum")
+_calc_min = _Reducer("min")
+_calc_max = _Reducer("max")
+_calc_std = _Reducer("std")
+_calc_range = _Reducer("range")
+_calc_var = _Reducer("var")
+_REDUCERS = {r.stat: r for r in (_calc_mean, _calc_sum, _calc_min, _calc_max, _calc_std,
+                                 _calc_range, _calc_var)}
+
+
+def _stat_of(func):
+    if isinstance(func, _Reducer):
+        return func.stat
+    if isinstance(func, str) and func in _REDUCERS:
+        return func
+    name = getattr(func, "__name__", "")
+    if name.startswith("_calc_") and name[6:] in _REDUCERS:
+        return name[6:]
+    raise NotImplementedError(
+        "focal.apply on the B200 backend supports the built-in reducers only "
+        "(mean, sum, min, max, std, range, var); got %r" % (func,))
+
+
+# ----------------------------------------------------------------------------- mean
+def _mean_numpy(data, excludes):
+    """One pass on a host float64 raster (replaces focal.py:44 `_mean_numpy`)."""
+    return run_stencil_host("focal_mean_f64", data, aux=tuple(excludes), out_dtype=np.float64,
+                            in_dtype=np.float64)
+
+
+def _mean_cupy(data, excludes):
+    """One pass on a device raster (replaces focal.py:135 `_mean_cupy`): float32 like the
+    reference's GPU path, float64 if the input is float64."""
+    import torch
+    t = as_device_tensor(data)
+    ex = _dbl_array(tuple(excludes))
+    if t.dtype == torch.float64:
+        return run_stencil_device("xrs_focal_mean_f64", data, aux=ex, naux=len(excludes), dtype=torch.float64)
+    return run_stencil_device("xrs_focal_mean_f32", data, aux=ex, naux=len(excludes))
+
+
+def _mean(data, excludes):
+    mapper = ArrayTypeFunctionMapping(numpy_func=_mean_numpy, cupy_func=_mean_cupy)
+    return mapper(DataArray(data))(data, excludes)
+
+
+@supports_dataset
+def mean(agg, passes=1, excludes=[np.nan], name='mean'):
+    """3x3 NaN-skipping mean filter applied `passes` times; cells equal to an `excludes` value
+    are passed through (focal.py:162-265).  numpy-backed input -> float64 like the reference's
+    CPU path; device input -> float32 (float64 if the input is float64) like its GPU path."""
+    data = agg.data
+    excludes = tuple(excludes)
+    if len(excludes) > 8:
+        raise ValueError("at most 8 exclude values are supported")
+    if isinstance(data, np.ndarray):
+        if passes <= 1:
+            out = data.astype(float) if passes < 1 else _mean_numpy(data, excludes)
+        else:
+            # keep intermediate passes on the device: one upload, `passes` kernels, one download
+            import torch
+            cur = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float64)).cuda()
+            for _ in range(passes):
+                cur = _mean_cupy(cur, excludes)
+            out = cur.cpu().numpy()
+    elif is_device_array(data):
+        import torch
+        cur = as_device_tensor(data)
+        if cur.dtype not in (torch.float32, torch.float64):
+            cur = cur.to(torch.float32)
+        for _ in range(passes):
+            cur = _mean_cupy(cur, excludes)
+        out = like_container(cur, data)
+    else:
+        out = _mean(data, excludes)  # raises for unsupported kinds
+    return DataArray(out, name=name, dims=agg.dims, coords=agg.coords, attrs=agg.attrs)
+
+
+# ----------------------------------------------------------------------------- apply / stats
+def _apply_numpy(data, kernel, func):
+    """replaces focal.py:305 `_apply_numpy` (host raster)."""
+    k = np.ascontiguousarray(kernel, dtype=np.float64)
+    return run_stencil_host("focal_stat", data, (k.shape[0], k.shape[1], _lib.STATS[_stat_of(func)]),
+                            aux=k.ravel())
+
+
+def _apply_cupy(data, kernel, func):
+    """device raster -> xrs_focal_stat_f32 with the CPU (NaN-skipping) semantics."""
+    k = np.ascontiguousarray(kernel, dtype=np.float64)
+    return run_stencil_device("xrs_focal_stat_f32", data, aux=k.ctypes.data_as(ctypes.c_void_p),
+                              extra_ints=(k.shape[0], k.shape[1], _lib.STATS[_stat_of(func)]))
+
+
+def apply(raster, kernel, func=_calc_mean, name='focal_apply'):
+    """Reducer over the cells where `kernel == 1`, NaN and out-of-raster cells skipped
+    (focal.py:343-473)."""
+    if not isinstance(raster, DataArray):
+        raise TypeError("`raster` must be instance of DataArray")
+    if raster.ndim != 2:
+        raise ValueError("`raster` must be 2D")
+    kernel = custom_kernel(kernel)
+    mapper = ArrayTypeFunctionMapping(numpy_func=_apply_numpy, cupy_func=_apply_cupy)
+    out = mapper(raster)(raster.data, kernel, func)
+    return DataArray(out, name=name, coords=raster.coords, dims=raster.dims, attrs=raster.attrs)
+
+
+def focal_stats(agg, kernel, stats_funcs=['mean', 'max', 'min', 'range', 'std', 'var', 'sum']):
+    """Stack of focal statistics along a new 'stats' dimension (focal.py:800-878)."""
+    if not isinstance(agg, DataArray):
+        raise TypeError("`agg` must be instance of DataArray")
+    if agg.ndim != 2:
+        raise ValueError("`agg` must be 2D")
+    kernel = custom_kernel(kernel)
+    stats_aggs = []
+    for stats in stats_funcs:
+        if stats not in _REDUCERS:
+            raise ValueError("unknown focal statistic %r" % (stats,))
+        stats_aggs.append(apply(agg, kernel, func=_REDUCERS[stats]))
+    return concat(stats_aggs, pd.Index(stats_funcs, name='stats', dtype=object))

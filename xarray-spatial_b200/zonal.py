@@ -1,0 +1,269 @@
+"""xrspatial.zonal.stats on the B200 backend (reference: zonal.py:422-667).
+
+One streaming pass of xrs_zonal_partials_ex produces per-zone count / sum / sum-of-squares /
+min / max partials; mean, std (ddof=0) and var are finalised from
+them in float64 on the host.  With `comm` (a torch.distributed process group) the partials of
+row-striped rasters are combined with AllReduce before finalisation.
+"""
+import ctypes
+
+import numpy as np
+import pandas as pd
+
+from . import _lib
+from ._xr import DataArray, Dataset
+from .utils import (ArrayTypeFunctionMapping, as_device_tensor, is_device_array, like_container,
+                    stream_ptr, validate_arrays)
+
+_DEFAULT_STATS = ("mean", "max", "min", "sum", "std", "var", "count", "majority")
+_PARTIAL_STATS = ("mean", "max", "min", "sum", "std", "var", "count")
+_TORCH_DT = None
+
+
+def _dtype_code(t):
+    import torch
+    return {torch.float32: 0, torch.float64: 1, torch.int32: 2, torch.int64: 3}.get(t.dtype)
+
+
+def _prepare(t, allow):
+    """Cast a device tensor to a dtype the kernel reads natively."""
+    import torch
+    if t.dtype in allow:
+        return t.contiguous()
+    if t.dtype.is_floating_point:
+        return t.to(torch.float64 if t.dtype == torch.float64 else torch.float32).contiguous()
+    if t.dtype in (torch.int8, torch.int16, torch.uint8, torch.bool):
+        return t.to(torch.int32).contiguous()
+    return t.to(torch.int64).contiguous()
+
+
+def discover_zone_ids(zones_t):
+    """Sorted unique finite zone ids of a device zones raster, as a numpy array in the raster's
+    dtype (zonal.py:290 `np.unique(zones[np.isfinite(zones)])`)."""
+    import torch
+    if zones_t.numel() == 0:
+        return np.empty((0,), dtype=np.float64)
+    if not zones_t.dtype.is_floating_point:
+        zmin, zmax = torch.aminmax(zones_t)
+        zmin, zmax = int(zmin.item()), int(zmax.item())
+        if zmax - zmin < (1 << 26):
+            # presence table over the compact id range (no sort of the raster)
+            present = torch.zeros(zmax - zmin + 1, dtype=torch.bool, device=zones_t.device)
+            present[(zones_t.reshape(-1) - zmin).long()] = True
+            ids = torch.nonzero(present).reshape(-1) + zmin
+            return ids.cpu().numpy()
+        return torch.unique(zones_t).cpu().numpy()
+    flat = zones_t.reshape(-1)
+    return torch.unique(flat[torch.isfinite(flat)]).cpu().numpy()
+
+
+def zonal_partials(zones_t, values_t, ids, nodata_values=None, pivot=None, comm=None):
+    """Run the kernel; returns dict of numpy arrays (count int64; s1, s2, min, max float64) and
+    the pivot used.  ids: sorted numpy array of candidate zone ids."""
+    import torch
+    dev = values_t.device
+    nz = len(ids)
+    ids_t = torch.as_tensor(np.asarray(ids, dtype=np.float64), device=dev)
+    if pivot is None:
+        # one global shift keeps sum((v-p)^2) well conditioned; a strided sample is enough
+        flat = values_t.reshape(-1)
+        step = max(1, flat.numel() // 65536)
+        sample = flat[::step].to(torch.float64)
+        sample = sample[torch.isfinite(sample)]
+        p0 = float(sample.mean().item()) if sample.numel() else 0.0
+        if comm is not None:
+            import torch.distributed as dist
+            pt = torch.tensor([p0], dtype=torch.float64, device=dev)
+            dist.broadcast(pt, src=dist.get_global_rank(comm, 0) if hasattr(dist, "get_global_rank") else 0,
+                           group=comm)
+            p0 = float(pt.item())
+        pivot = np.full(nz, p0, dtype=np.float64)
+    piv_t = torch.as_tensor(np.asarray(pivot, dtype=np.float64), device=dev)
+    count = torch.empty(nz, dtype=torch.int64, device=dev)
+    s1 = torch.empty(nz, dtype=torch.float64, device=dev)
+    s2 = torch.empty(nz, dtype=torch.float64, device=dev)
+    vmin = torch.empty(nz, dtype=torch.float64, device=dev)
+    vmax = torch.empty(nz, dtype=torch.float64, device=dev)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    use_lut, lut_base = 0, 0
+    if nz and not zones_t.dtype.is_floating_point:
+        lo, hi = int(ids[0]), int(ids[-1])
+        if hi - lo < 8192 and nz <= 2048:
+            use_lut, lut_base = 1, lo
+    with torch.cuda.device(dev):
+        st = stream_ptr(values_t)
+        if nz:
+            _lib.call("xrs_zonal_init", P(count), P(s1), P(s2), P(vmin), P(vmax), nz, st)
+            _lib.call("xrs_zonal_partials_ex", P(values_t), _dtype_code(values_t), P(zones_t),
+                      _dtype_code(zones_t), values_t.numel(), P(ids_t), nz, P(piv_t),
+                      0 if nodata_values is None else 1,
+                      0.0 if nodata_values is None else float(nodata_values), use_lut, lut_base,
+                      P(count), P(s1), P(s2), P(vmin), P(vmax), st)
+    if comm is not None and nz:
+        import torch.distributed as dist
+        dist.all_reduce(count, op=dist.ReduceOp.SUM, group=comm)
+        dist.all_reduce(s1, op=dist.ReduceOp.SUM, group=comm)
+        dist.all_reduce(s2, op=dist.ReduceOp.SUM, group=comm)
+        dist.all_reduce(vmin, op=dist.ReduceOp.MIN, group=comm)
+        dist.all_reduce(vmax, op=dist.ReduceOp.MAX, group=comm)
+    return dict(count=count.cpu().numpy(), s1=s1.cpu().numpy(), s2=s2.cpu().numpy(),
+                min=vmin.cpu().numpy(), max=vmax.cpu().numpy()), np.asarray(pivot, dtype=np.float64)
+
+
+def finalize(part, pivot, stats_funcs):
+    """dict stat -> float64 column; zones without valid cells are NaN (zonal.py:153-162)."""
+    cnt = part["count"].astype(np.float64)
+    ok = cnt > 0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        m1 = part["s1"] / cnt
+        cols = {}
+        for s in stats_funcs:
+            if s == "mean":
+                c = pivot + m1
+            elif s == "sum":
+                c = pivot * cnt + part["s1"]
+            elif s in ("var", "std"):
+                c = np.maximum(part["s2"] / cnt - m1 * m1, 0.0)
+                if s == "std":
+                    c = np.sqrt(c)
+            elif s == "count":
+                c = cnt.copy()
+            elif s == "max":
+                c = part["max"].copy()
+            elif s == "min":
+                c = part["min"].copy()
+            else:
+                raise ValueError("Invalid stat name. %s option not supported." % s)
+            c = np.where(ok, c, np.nan)
+            cols[s] = c
+    return cols
+
+
+def _stats_device(zones, values, zone_ids, stats_funcs, nodata_values, return_type='pandas.DataFrame',
+                  comm=None):
+    """Device runner (replaces zonal.py:335 `_stats_cupy`)."""
+    import torch
+    zt = _prepare(as_device_tensor(zones), (torch.int32, torch.int64, torch.float32, torch.float64))
+    vt = _prepare(as_device_tensor(values), (torch.float32, torch.float64))
+    if vt.dtype not in (torch.float32, torch.float64):
+        vt = vt.to(torch.float64)
+    if len(vt.shape) > 2:
+        raise TypeError('3D inputs not supported for the device backend')
+    names = list(stats_funcs)
+    if "majority" in names:
+        raise NotImplementedError("'majority' is not available on the B200 backend yet "
+                                  "(SURVEY.md section 8f rank 2)")
+    unique_zones = discover_zone_ids(zt)
+    if comm is not None:
+        # union of the ids seen by every stripe
+        import torch.distributed as dist
+        gathered = [None] * dist.get_world_size(comm)
+        dist.all_gather_object(gathered, unique_zones, group=comm)
+        unique_zones = np.unique(np.concatenate([np.asarray(g) for g in gathered]))
+    zdtype = unique_zones.dtype
+    if zone_ids is None:
+        sel = unique_zones
+    else:
+        sel = np.array([z for z in np.unique(zone_ids) if z in unique_zones], dtype=zdtype)
+    part, pivot = zonal_partials(zt, vt, sel, nodata_values, comm=comm)
+    if vt.dtype == torch.float64 and len(sel) and any(s in names for s in ("std", "var")):
+        # second pass about the per-zone means: numpy's two-pass variance, to ~1e-15
+        cnt = part["count"].astype(np.float64)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            means = np.where(cnt > 0, pivot + part["s1"] / cnt, 0.0)
+        part2, piv2 = zonal_partials(zt, vt, sel, nodata_values, pivot=means, comm=comm)
+        part = dict(part)
+        cols = finalize(part, pivot, [s for s in names if s not in ("std", "var")])
+        cols.update(finalize(part2, piv2, [s for s in names if s in ("std", "var")]))
+    else:
+        cols = finalize(part, pivot, names)
+    if return_type == 'pandas.DataFrame':
+        d = {"zone": sel}
+        for s in names:
+            d[s] = cols[s]
+        return pd.DataFrame(d)
+    # broadcast every stat back onto the raster (zonal.py:313-331)
+    H, W = vt.shape
+    out = torch.full((len(names), H * W), float("nan"), dtype=torch.float64, device=vt.device)
+    if len(sel):
+        ids_t = torch.as_tensor(np.asarray(sel, dtype=np.float64), device=vt.device)
+        zf = zt.reshape(-1).to(torch.float64)
+        idx = torch.searchsorted(ids_t, zf).clamp_(max=len(sel) - 1)
+        hit = ids_t[idx] == zf
+        for i, s in enumerate(names):
+            table = torch.as_tensor(cols[s], device=vt.device)
+            out[i] = torch.where(hit, table[idx], out[i])
+    return like_container(out.reshape(len(names), H, W), values)
+
+
+def _stats_host(zones, values, zone_ids, stats_funcs, nodata_values, return_type='pandas.DataFrame'):
+    """numpy runner (replaces zonal.py:280 `_stats_numpy`): upload, same device pass."""
+    import torch
+    zt = torch.from_numpy(np.ascontiguousarray(zones)).cuda()
+    vt = torch.from_numpy(np.ascontiguousarray(values)).cuda()
+    res = _stats_device(zt, vt, zone_ids, stats_funcs, nodata_values, return_type)
+    if return_type != 'pandas.DataFrame':
+        res = res.cpu().numpy()
+    else:
+        res["zone"] = res["zone"].astype(np.asarray(zones).dtype)
+    return res
+
+
+def stats(zones, values, zone_ids=None,
+          stats_funcs=["mean", "max", "min", "sum", "std", "var", "count"],
+          nodata_values=None, return_type='pandas.DataFrame', comm=None):
+    """Per-zone summary statistics (zonal.py:422-667).
+
+    Differences from the reference, all explicit: `stats_funcs` must name built-in statistics
+    (custom callables cannot run on the device), `majority` is not available yet, and the
+    default list therefore omits it.  `comm` (optional torch.distributed group) marks `zones`
+    and `values` as this rank's row stripe of a larger raster.
+    """
+    if isinstance(values, Dataset):
+        if return_type != 'pandas.DataFrame':
+            raise ValueError("return_type must be 'pandas.DataFrame' when values is a Dataset")
+        dfs = []
+        for var_name in values.data_vars:
+            df = stats(zones, values[var_name], zone_ids, stats_funcs, nodata_values, 'pandas.DataFrame')
+            df = df.rename(columns={c: f'{var_name}_{c}' for c in df.columns if c != 'zone'})
+            dfs.append(df)
+        result = dfs[0]
+        for df in dfs[1:]:
+            result = result.merge(df, on='zone', how='outer')
+        return result
+
+    validate_arrays(zones, values)
+    for nm, arr in (("zones", zones), ("values", values)):
+        dt = arr.data.dtype
+        kind = getattr(dt, "kind", None)
+        if kind is None:  # torch dtype
+            ok = dt.is_floating_point or "int" in str(dt)
+        else:
+            ok = kind in "iuf"
+        if not ok:
+            raise ValueError("`%s` must be an array of integers or floats." % nm)
+
+    if isinstance(stats_funcs, dict):
+        bad = [k for k, f in stats_funcs.items() if k not in _DEFAULT_STATS]
+        if bad:
+            raise NotImplementedError("custom statistics %r cannot run on the B200 backend" % (bad,))
+        names = list(stats_funcs.keys())
+    else:
+        names = list(stats_funcs)
+    for s in names:
+        if s not in _DEFAULT_STATS:
+            raise ValueError(f"Invalid stat name. {s} option not supported.")
+
+    if comm is not None:
+        result = _stats_device(zones.data, values.data, zone_ids, names, nodata_values, return_type, comm)
+    else:
+        mapper = ArrayTypeFunctionMapping(
+            numpy_func=lambda *a: _stats_host(*a, return_type=return_type),
+            cupy_func=lambda *a: _stats_device(*a, return_type=return_type))
+        result = mapper(values)(zones.data, values.data, zone_ids, names, nodata_values)
+
+    if return_type == 'xarray.DataArray':
+        coords = {'stats': names}
+        coords.update(values.coords)
+        return DataArray(result, coords=coords, dims=('stats',) + tuple(values.dims), attrs=values.attrs)
+    return result

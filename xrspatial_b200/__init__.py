@@ -1,0 +1,8 @@
+"""Importable alias of the package directory `xarray-spatial_b200/` (a hyphen is not a valid
+module name): `import xrspatial_b200` exposes that directory's modules."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "xarray-spatial_b200")
+__path__ = [_real]
+with open(_os.path.join(_real, "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
