@@ -91,6 +91,11 @@ int xrs_focal_mean_f32(const float *in, int64_t in_pitch, float *out, int64_t ou
                        int64_t H, int64_t W, const double *excludes, int n_ex, xrs_stream_t s);
 int xrs_focal_mean_f64(const double *in, int64_t in_pitch, double *out, int64_t out_pitch,
                        int64_t H, int64_t W, const double *excludes, int n_ex, xrs_stream_t s);
+/* float32 in, float64 out: what focal.mean's `agg.data.astype(float)` (focal.py:257) yields for
+ * a float32 raster, without a separate widening pass */
+int xrs_focal_mean_f32_f64(const float *in, int64_t in_pitch, double *out, int64_t out_pitch,
+                           int64_t H, int64_t W, const double *excludes, int n_ex,
+                           xrs_stream_t s);
 /* convolution._convolve_2d_cupy (convolution.py:368-374) / `_convolve_2d_numpy` (:285-313):
  * correlation with a host float64 kernel (kh, kw odd, <= 63); NaN ring of (kh/2, kw/2). */
 int xrs_convolve2d_f32(const float *in, int64_t in_pitch, float *out, int64_t out_pitch,
@@ -162,9 +167,10 @@ int xrs_zonal_partials_ex(const void *values, int values_dtype, const void *zone
 enum xrs_op {
     XRS_OP_SLOPE = 0, XRS_OP_ASPECT = 1, XRS_OP_CURVATURE = 2, XRS_OP_HILLSHADE = 3,
     XRS_OP_FOCAL_MEAN = 4, XRS_OP_CONVOLVE = 5, XRS_OP_FOCAL_STAT = 6,
-    XRS_OP_FOCAL_MEAN_F64 = 7 /* in/out are double */
+    XRS_OP_FOCAL_MEAN_F64 = 7,     /* in/out are double */
+    XRS_OP_FOCAL_MEAN_F32_F64 = 8  /* in float, out double */
 };
-/* in/out: float32 rasters (float64 for XRS_OP_FOCAL_MEAN_F64), contiguous rows.
+/* in/out: float32 rasters (see the two FOCAL_MEAN_F* ops for float64), contiguous rows.
  * p: slope {csx, csy}; curvature {cellsize}; hillshade {azimuth, altitude};
  *    convolve {kh, kw}; focal stat {kh, kw, stat}.  aux: excludes / kernel (host). */
 int xrs_host_stencil(int op, const void *in, void *out, int64_t H, int64_t W, const double *p,

@@ -1,0 +1,155 @@
+"""CPU-only tests of the Python host layer: resolution, kernels, validation and error types
+mirror the reference's tests (test_focal.py:178-197, test_utils.py, test_dataset_support.py)."""
+import numpy as np
+import pytest
+
+import xrspatial_b200 as xb
+from xrspatial_b200 import convolution, focal, utils, zonal
+from xrspatial_b200.dataset_support import supports_dataset, supports_dataset_bands
+
+
+def raster(data, **kw):
+    r = xb.DataArray(np.asarray(data), dims=("y", "x"), **kw)
+    return r
+
+
+def test_resolution_from_attrs_and_coords():
+    r = raster(np.zeros((4, 5)), attrs={"res": (0.5, 2.0)})
+    assert utils.get_dataarray_resolution(r) == (0.5, 2.0)
+    r = raster(np.zeros((4, 5)), attrs={"res": 3})
+    assert utils.get_dataarray_resolution(r) == (3, 3)
+    r = raster(np.zeros((4, 5)))
+    r["y"] = np.linspace(30, 0, 4)     # descending y like create_test_raster (general_checks.py:30-52)
+    r["x"] = np.linspace(0, 8, 5)
+    assert utils.get_dataarray_resolution(r) == (2.0, 10.0)
+    r.attrs["res"] = "bogus"           # falls back to the coordinates (utils.py:268-275)
+    assert utils.get_dataarray_resolution(r) == (2.0, 10.0)
+
+
+def test_calc_cellsize_units():
+    r = raster(np.ones((100, 200)), attrs={"res": (0.5, 0.5)})
+    assert convolution.calc_cellsize(r) == (0.5, 0.5)
+    r = raster(np.ones((100, 200)), attrs={"unit": "km"})
+    r["y"] = np.linspace(1, 100, 100)
+    r["x"] = np.linspace(1, 200, 200)
+    cx, cy = convolution.calc_cellsize(r)
+    assert cx == 1000.0 and cy == 1000.0
+
+
+def test_kernels(known):
+    # test_focal.py:190-197
+    np.testing.assert_array_equal(convolution.circle_kernel(1, 1, 1), known["focal.kernel_circle_1_1_1"])
+    np.testing.assert_array_equal(convolution.annulus_kernel(2, 2, 2, 1), known["focal.kernel_annulus_2_2_2_1"])
+    k = convolution.circle_kernel(1, 1, "3m")
+    assert k.shape == (7, 7) and k[3].sum() == 7 and k[0].sum() == 1
+    assert convolution.circle_kernel(10, 10, "0.03km").shape == (7, 7)
+    with pytest.raises(ValueError):
+        convolution.circle_kernel(1, 1, "3 parsecs")
+    with pytest.raises(ValueError):
+        convolution.circle_kernel(1, 1, -3)
+
+
+def test_custom_kernel_validation():
+    # test_focal.py:178-187
+    with pytest.raises(ValueError):
+        convolution.custom_kernel([[1, 0, 0], [0, 1, 0], [0, 0, 1]])
+    with pytest.raises(ValueError):
+        convolution.custom_kernel(np.ones((4, 6)))
+    k = np.ones((3, 5))
+    assert convolution.custom_kernel(k) is k
+
+
+def test_error_types_before_any_device_work():
+    r = raster(np.zeros((4, 4), np.float32), attrs={"res": (1, 1)})
+    with pytest.raises(ValueError):
+        xb.slope(r, method="spherical")                      # slope.py:334-337
+    with pytest.raises(NotImplementedError):
+        xb.slope(r, method="geodesic")
+    with pytest.raises(ValueError):
+        xb.aspect(r, method="nope")
+    with pytest.raises(RuntimeError):
+        xb.hillshade(r, shadows=True)                        # hillshade.py:176-178
+    with pytest.raises(TypeError):
+        focal.apply(np.zeros((4, 4)), np.ones((3, 3)))       # focal.py:447
+    with pytest.raises(ValueError):
+        focal.apply(xb.DataArray(np.zeros((2, 3, 4))), np.ones((3, 3)))
+    with pytest.raises(ValueError):
+        focal.apply(r, np.ones((2, 2)))
+    with pytest.raises(NotImplementedError):
+        focal.apply(r, np.ones((3, 3)), func=lambda x: 0)    # only built-in reducers cross the C ABI
+    with pytest.raises(ValueError):
+        xb.savi(r, r, soil_factor=1.5)                       # multispectral.py:999-1000
+    with pytest.raises(ValueError):
+        xb.evi(r, r, r, gain=-1)
+    with pytest.raises(ValueError):
+        xb.evi(r, r, r, c1="6")
+    with pytest.raises(ValueError):
+        xb.ndvi(r, raster(np.zeros((4, 5), np.float32)))     # utils.py:155 shapes
+    with pytest.raises(ValueError):
+        xb.zonal_stats(r, r, stats_funcs=["median"])         # zonal.py:639-642
+    with pytest.raises(ValueError):
+        xb.zonal_stats(raster(np.zeros((4, 4), dtype=bool)), r)
+
+
+def test_unsupported_array_type():
+    class Odd(object):
+        shape = (2, 2)
+        dtype = np.dtype("f4")
+    mapper = utils.ArrayTypeFunctionMapping(numpy_func=lambda *a: 1, cupy_func=lambda *a: 2)
+    assert mapper(raster(np.zeros((2, 2))))() == 1
+    holder = type("H", (), {"data": Odd()})()
+    with pytest.raises(TypeError):
+        mapper(holder)
+
+
+def test_supports_dataset_decorators():
+    # test_dataset_support.py: per-variable call, name injection, attrs kept, band kwargs
+    calls = []
+
+    @supports_dataset
+    def f(agg, name="f"):
+        calls.append(name)
+        return xb.DataArray(agg.data + 1, dims=agg.dims, name=name)
+
+    ds = xb.Dataset({"a": raster(np.zeros((2, 2))), "b": raster(np.ones((2, 2)))}, attrs={"k": 1})
+    out = f(ds)
+    assert isinstance(out, xb.Dataset) and list(out.data_vars) == ["a", "b"] and out.attrs == {"k": 1}
+    assert calls == ["a", "b"] and out["b"].data[0, 0] == 2 and out["a"].name == "a"
+
+    @supports_dataset_bands(nir="nir_agg", red="red_agg")
+    def g(nir_agg, red_agg, name="g", extra=0):
+        return (nir_agg.data - red_agg.data + extra).sum()
+
+    assert g(ds, nir="b", red="a", extra=1) == 8
+    with pytest.raises(TypeError):
+        g(ds, nir="b")
+    with pytest.raises(ValueError):
+        g(ds, nir="b", red="zzz")
+
+
+def test_zonal_finalize_matches_numpy():
+    """finalize() turns (count, shifted sums, min, max) partials into the reference's columns."""
+    rng = np.random.default_rng(3)
+    vals = [rng.normal(1000, 5, 50), rng.normal(-3, 1, 7), np.array([]), np.array([42.0])]
+    pivot = np.full(4, 900.0)
+    part = dict(count=np.array([len(v) for v in vals], dtype=np.int64),
+                s1=np.array([(v - 900.0).sum() for v in vals]),
+                s2=np.array([((v - 900.0) ** 2).sum() for v in vals]),
+                min=np.array([v.min() if len(v) else np.inf for v in vals]),
+                max=np.array([v.max() if len(v) else -np.inf for v in vals]))
+    cols = zonal.finalize(part, pivot, ["mean", "max", "min", "sum", "std", "var", "count"])
+    for i, v in enumerate(vals):
+        if len(v) == 0:
+            assert all(np.isnan(cols[c][i]) for c in cols)
+            continue
+        np.testing.assert_allclose(cols["mean"][i], v.mean(), rtol=1e-13)
+        np.testing.assert_allclose(cols["sum"][i], v.sum(), rtol=1e-13)
+        np.testing.assert_allclose(cols["var"][i], v.var(), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(cols["std"][i], v.std(), rtol=1e-9, atol=1e-12)
+        assert cols["count"][i] == len(v) and cols["min"][i] == v.min() and cols["max"][i] == v.max()
+
+
+def test_split_rows():
+    from xrspatial_b200.stripes import split_rows
+    assert split_rows(10, 3) == [(0, 4), (4, 7), (7, 10)]
+    assert split_rows(65536, 8)[7] == (57344, 65536)

@@ -11,7 +11,7 @@ SO_PATH = os.path.join(HERE, "libxrs_b200.so")
 
 XRS_OK, XRS_EINVAL, XRS_ECUDA, XRS_EUNSUPPORTED, XRS_ENOMEM = 0, -1, -2, -3, -4
 OPS = dict(slope=0, aspect=1, curvature=2, hillshade=3, focal_mean=4, convolve=5, focal_stat=6,
-           focal_mean_f64=7)
+           focal_mean_f64=7, focal_mean_f32_f64=8)
 STATS = dict(mean=0, sum=1, min=2, max=3, std=4, range=5, var=6)
 DTYPES = dict(float32=0, float64=1, int32=2, int64=3)
 
@@ -40,6 +40,7 @@ def _declare(lib):
         "xrs_surface_suite_f32": [P, I64, P, P, P, P, I64, I64, I64, D, D, D, D, P],
         "xrs_focal_mean_f32": [P, I64, P, I64, I64, I64, P, I, P],
         "xrs_focal_mean_f64": [P, I64, P, I64, I64, I64, P, I, P],
+        "xrs_focal_mean_f32_f64": [P, I64, P, I64, I64, I64, P, I, P],
         "xrs_convolve2d_f32": [P, I64, P, I64, I64, I64, P, I, I, P],
         "xrs_focal_stat_f32": [P, I64, P, I64, I64, I64, P, I, I, I, P],
         "xrs_normalized_ratio_f32": [P, P, P, I64, P],

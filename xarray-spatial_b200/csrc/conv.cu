@@ -28,6 +28,9 @@ struct MaskBits {
 struct TileGeom {
     int64_t H, W;
     int kh, kw, ry, rx;
+    int pad;       // cells loaded left of the tile: rx rounded up to 4 (TMA box starts must stay
+                   // 16-byte aligned in the innermost dimension)
+    int off;       // pad - rx: column offset of tap 0 inside the shared tile
     int sw;        // shared tile width (cells), multiple of 4
     int sh;        // shared tile height = kTileH + kh - 1
     int tiles_x, tiles_y;
@@ -41,7 +44,7 @@ __device__ __forceinline__ void load_tile_tma(const CUtensorMap *tmap, float *ti
         const int nbox = (g.sh + g.box_h - 1) / g.box_h;
         mbar_arrive_expect_tx(bar, (uint32_t)(nbox * g.box_h * g.sw * sizeof(float)));
         for (int b = 0; b < nbox; ++b)
-            tma_load_2d(tile32 + (size_t)b * g.box_h * g.sw, tmap, bar, tx0 - g.rx, ty0 - g.ry + b * g.box_h);
+            tma_load_2d(tile32 + (size_t)b * g.box_h * g.sw, tmap, bar, tx0 - g.pad, ty0 - g.ry + b * g.box_h);
     }
     mbar_wait(bar, parity);
 }
@@ -87,7 +90,8 @@ conv2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
         const int rows_in = 4 + g.kh - 1;
         for (int j = 0; j < rows_in; ++j) {
             const double *rowp = tile64 + (size_t)(ty * 4 + j) * g.sw + 4 * tx;
-            for (int kb = 0; kb < g.kw; kb += 4) {
+            // taps are indexed from the aligned tile origin: tap kx sits at column kx + off
+            for (int kb = 0; kb < g.off + g.kw; kb += 4) {
                 double v[8];
                 const double2 q0 = *reinterpret_cast<const double2 *>(rowp + kb);
                 const double2 q1 = *reinterpret_cast<const double2 *>(rowp + kb + 2);
@@ -101,8 +105,9 @@ conv2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
                     if (ky >= 0 && ky < g.kh) {
 #pragma unroll
                         for (int tt = 0; tt < 4; ++tt) {
-                            if (kb + tt < g.kw) {
-                                const double wv = cw.w[ky * g.kw + kb + tt];
+                            const int kx = kb + tt - g.off;
+                            if (kx >= 0 && kx < g.kw) {
+                                const double wv = cw.w[ky * g.kw + kx];
 #pragma unroll
                                 for (int c = 0; c < 4; ++c) acc[r][c] = fma(wv, v[c + tt], acc[r][c]);
                             }
@@ -219,7 +224,7 @@ focal_stat_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             const int lx = o % kTileW, ly = o / kTileW;
             const int64_t xo = (int64_t)x0 + lx, yo = (int64_t)y0 + ly;
             if (xo < g.W && yo < g.H) {
-                const float *base = tile32 + (size_t)ly * g.sw + lx;
+                const float *base = tile32 + (size_t)ly * g.sw + lx + g.off;
                 const int sw = g.sw;
                 auto fetch = [base, sw](int ky, int kx) { return base[ky * sw + kx]; };
                 out[yo * out_pitch_elems + xo] = focal_reduce(fetch, mask, g.kh, g.kw, stat);
@@ -260,8 +265,10 @@ static int check_common(const float *in, int64_t in_pitch, float *out, int64_t o
 static bool tile_geom(TileGeom &g, CUtensorMap *tmap, const float *in, int64_t in_pitch, float *out,
                       int64_t out_pitch, int64_t H, int64_t W, int kh, int kw) {
     g.H = H; g.W = W; g.kh = kh; g.kw = kw; g.ry = kh / 2; g.rx = kw / 2;
-    // the 8-wide chunk loads of the convolution reach 4*31 + 4*((kw-1)/4) + 7 cells into a row
-    g.sw = ((kTileW + ((kw + 3) / 4) * 4 + 4) + 3) / 4 * 4;
+    g.pad = (g.rx + 3) / 4 * 4;
+    g.off = g.pad - g.rx;
+    // the 8-wide chunk loads of the convolution reach 4*31 + 4*((off+kw-1)/4) + 7 cells into a row
+    g.sw = kTileW + ((g.off + kw + 3) / 4) * 4 + 4;
     g.sh = kTileH + kh - 1;
     g.tiles_x = (int)((W + kTileW - 1) / kTileW);
     g.tiles_y = (int)((H + kTileH - 1) / kTileH);

@@ -50,21 +50,24 @@ static int ensure_cap(void **p, size_t *cap, size_t need) {
     return XRS_OK;
 }
 
-static int run_op(int op, const void *din, void *dout, int64_t pitch, int64_t h, int64_t W, const double *p,
+static int run_op(int op, const void *din, void *dout, int64_t pitch, int64_t opitch, int64_t h, int64_t W,
+                  const double *p,
                   const double *aux, int naux, cudaStream_t s) {
     const float *fi = (const float *)din;
     float *fo = (float *)dout;
     switch (op) {
-        case XRS_OP_SLOPE: return xrs_slope_f32(fi, pitch, fo, pitch, h, W, p[0], p[1], s);
-        case XRS_OP_ASPECT: return xrs_aspect_f32(fi, pitch, fo, pitch, h, W, s);
-        case XRS_OP_CURVATURE: return xrs_curvature_f32(fi, pitch, fo, pitch, h, W, p[0], s);
-        case XRS_OP_HILLSHADE: return xrs_hillshade_f32(fi, pitch, fo, pitch, h, W, p[0], p[1], s);
-        case XRS_OP_FOCAL_MEAN: return xrs_focal_mean_f32(fi, pitch, fo, pitch, h, W, aux, naux, s);
+        case XRS_OP_SLOPE: return xrs_slope_f32(fi, pitch, fo, opitch, h, W, p[0], p[1], s);
+        case XRS_OP_ASPECT: return xrs_aspect_f32(fi, pitch, fo, opitch, h, W, s);
+        case XRS_OP_CURVATURE: return xrs_curvature_f32(fi, pitch, fo, opitch, h, W, p[0], s);
+        case XRS_OP_HILLSHADE: return xrs_hillshade_f32(fi, pitch, fo, opitch, h, W, p[0], p[1], s);
+        case XRS_OP_FOCAL_MEAN: return xrs_focal_mean_f32(fi, pitch, fo, opitch, h, W, aux, naux, s);
         case XRS_OP_FOCAL_MEAN_F64:
-            return xrs_focal_mean_f64((const double *)din, pitch, (double *)dout, pitch, h, W, aux, naux, s);
-        case XRS_OP_CONVOLVE: return xrs_convolve2d_f32(fi, pitch, fo, pitch, h, W, aux, (int)p[0], (int)p[1], s);
+            return xrs_focal_mean_f64((const double *)din, pitch, (double *)dout, opitch, h, W, aux, naux, s);
+        case XRS_OP_FOCAL_MEAN_F32_F64:
+            return xrs_focal_mean_f32_f64(fi, pitch, (double *)dout, opitch, h, W, aux, naux, s);
+        case XRS_OP_CONVOLVE: return xrs_convolve2d_f32(fi, pitch, fo, opitch, h, W, aux, (int)p[0], (int)p[1], s);
         case XRS_OP_FOCAL_STAT:
-            return xrs_focal_stat_f32(fi, pitch, fo, pitch, h, W, aux, (int)p[0], (int)p[1], (int)p[2], s);
+            return xrs_focal_stat_f32(fi, pitch, fo, opitch, h, W, aux, (int)p[0], (int)p[1], (int)p[2], s);
     }
     set_error("unknown op %d", op);
     return XRS_EINVAL;
@@ -79,8 +82,9 @@ extern "C" int xrs_host_stencil(int op, const void *in, void *out, int64_t H, in
     if (H <= 0 || W <= 0) return XRS_OK;
     XRS_REQUIRE(in && out, "NULL host pointer");
     XRS_REQUIRE(device >= 0 && device < 16, "device index out of range");
-    XRS_REQUIRE(op >= XRS_OP_SLOPE && op <= XRS_OP_FOCAL_MEAN_F64, "unknown op");
-    const int esz = (op == XRS_OP_FOCAL_MEAN_F64) ? 8 : 4;
+    XRS_REQUIRE(op >= XRS_OP_SLOPE && op <= XRS_OP_FOCAL_MEAN_F32_F64, "unknown op");
+    const int esz = (op == XRS_OP_FOCAL_MEAN_F64) ? 8 : 4;                                       // input
+    const int osz = (op == XRS_OP_FOCAL_MEAN_F64 || op == XRS_OP_FOCAL_MEAN_F32_F64) ? 8 : 4;  // output
     int radius = 1;
     if (op == XRS_OP_CONVOLVE || op == XRS_OP_FOCAL_STAT) {
         XRS_REQUIRE(p && aux, "kernel parameters missing");
@@ -99,13 +103,13 @@ extern "C" int xrs_host_stencil(int op, const void *in, void *out, int64_t H, in
     if (rc) { cudaSetDevice(prev); return rc; }
 
     // device row pitch: multiple of 16 bytes so the TMA kernels apply whenever W % 4 == 0
-    const int64_t row_bytes = W * esz;
-    const int64_t pitch = (row_bytes + 15) / 16 * 16;
+    const int64_t row_bytes = W * esz, orow_bytes = W * osz;
+    const int64_t pitch = (row_bytes + 15) / 16 * 16, opitch = (orow_bytes + 15) / 16 * 16;
     int64_t rows = (32LL << 20) / pitch;
     if (rows < 8 * radius + 8) rows = 8 * radius + 8;
     if (rows > H) rows = H;
     const int64_t n_chunks = (H + rows - 1) / rows;
-    const size_t cap = (size_t)(rows + 2 * radius) * pitch;
+    const size_t cap = (size_t)(rows + 2 * radius) * pitch, ocap = (size_t)(rows + 2 * radius) * opitch;
 
     for (int64_t ci = 0; ci < n_chunks && rc == XRS_OK; ++ci) {
         Slot &s = c.slot[ci % 3];
@@ -117,20 +121,21 @@ extern "C" int xrs_host_stencil(int op, const void *in, void *out, int64_t H, in
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaEventSynchronize"); break; }
         rc = ensure_cap(&s.din, &s.cap_in, cap);
         if (rc) break;
-        rc = ensure_cap(&s.dout, &s.cap_out, cap);
+        rc = ensure_cap(&s.dout, &s.cap_out, ocap);
         if (rc) break;
         e = cudaMemcpy2DAsync(s.din, pitch, (const char *)in + a0 * row_bytes, row_bytes, row_bytes, h,
                               cudaMemcpyHostToDevice, c.s_in);
         if (e == cudaSuccess) e = cudaEventRecord(s.in_done, c.s_in);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(c.s_k, s.in_done, 0);
         if (e != cudaSuccess) { rc = cuda_fail(e, "H2D enqueue"); break; }
-        rc = run_op(op, s.din, s.dout, pitch, h, W, p, aux, naux, c.s_k);
+        rc = run_op(op, s.din, s.dout, pitch, opitch, h, W, p, aux, naux, c.s_k);
         if (rc) break;
         e = cudaEventRecord(s.k_done, c.s_k);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(c.s_out, s.k_done, 0);
         if (e == cudaSuccess)
-            e = cudaMemcpy2DAsync((char *)out + r0 * row_bytes, row_bytes, (const char *)s.dout + (r0 - a0) * pitch,
-                                  pitch, row_bytes, r1 - r0, cudaMemcpyDeviceToHost, c.s_out);
+            e = cudaMemcpy2DAsync((char *)out + r0 * orow_bytes, orow_bytes,
+                                  (const char *)s.dout + (r0 - a0) * opitch, opitch, orow_bytes, r1 - r0,
+                                  cudaMemcpyDeviceToHost, c.s_out);
         if (e == cudaSuccess) e = cudaEventRecord(s.out_done, c.s_out);
         if (e != cudaSuccess) { rc = cuda_fail(e, "D2H enqueue"); break; }
     }

@@ -24,10 +24,10 @@ static HillshadeOp::Params hillshade_params(double azimuth, double angle_altitud
     return p;
 }
 
-template <typename T, int ROWS, int STAGES>
-static int focal_mean_impl(const T *in, int64_t in_pitch, T *out, int64_t out_pitch, int64_t H, int64_t W,
+template <typename T, typename TOUT, int ROWS, int STAGES>
+static int focal_mean_impl(const T *in, int64_t in_pitch, TOUT *out, int64_t out_pitch, int64_t H, int64_t W,
                            const double *excludes, int n_ex, xrs_stream_t s) {
-    using Op = FocalMeanOp<T>;
+    using Op = FocalMeanOp<T, TOUT>;
     XRS_REQUIRE(n_ex >= 0 && n_ex <= Op::kMaxEx, "at most 8 exclude values are supported");
     XRS_REQUIRE(n_ex == 0 || excludes != nullptr, "excludes is NULL");
     typename Op::Params p;
@@ -38,7 +38,7 @@ static int focal_mean_impl(const T *in, int64_t in_pitch, T *out, int64_t out_pi
         if (excludes[i] != excludes[i]) p.ex_nan = 1;
         else p.ex[p.n_ex++] = excludes[i];
     }
-    T *outs[1] = {out};
+    TOUT *outs[1] = {out};
     return launch_stencil3<Op, ROWS, STAGES>(in, in_pitch, p, outs, out_pitch, H, W, (cudaStream_t)s);
 }
 
@@ -96,12 +96,17 @@ int xrs_surface_suite_f32(const float *in, int64_t in_pitch, float *slope_out, f
 
 int xrs_focal_mean_f32(const float *in, int64_t in_pitch, float *out, int64_t out_pitch, int64_t H,
                        int64_t W, const double *excludes, int n_ex, xrs_stream_t s) {
-    return focal_mean_impl<float, kRowsF32, kStagesF32>(in, in_pitch, out, out_pitch, H, W, excludes, n_ex, s);
+    return focal_mean_impl<float, float, kRowsF32, kStagesF32>(in, in_pitch, out, out_pitch, H, W, excludes, n_ex, s);
 }
 int xrs_focal_mean_f64(const double *in, int64_t in_pitch, double *out, int64_t out_pitch, int64_t H,
                        int64_t W, const double *excludes, int n_ex, xrs_stream_t s) {
-    return focal_mean_impl<double, kRowsF64, kStagesF64>(in, in_pitch, out, out_pitch, H, W, excludes, n_ex,
-                                                         s);
+    return focal_mean_impl<double, double, kRowsF64, kStagesF64>(in, in_pitch, out, out_pitch, H, W, excludes,
+                                                                 n_ex, s);
+}
+int xrs_focal_mean_f32_f64(const float *in, int64_t in_pitch, double *out, int64_t out_pitch, int64_t H,
+                           int64_t W, const double *excludes, int n_ex, xrs_stream_t s) {
+    return focal_mean_impl<float, double, kRowsF32, kStagesF32>(in, in_pitch, out, out_pitch, H, W, excludes,
+                                                                n_ex, s);
 }
 
 }  // extern "C"

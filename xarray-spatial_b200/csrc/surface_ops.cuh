@@ -238,9 +238,9 @@ __device__ __forceinline__ double div_count9(double s, int cnt) {
 // ------------------------------------------------------------------ focal.mean (focal.py:44-67)
 // 3x3 NaN-skipping mean over the window clamped to the raster (out-of-raster cells arrive
 // as NaN and are skipped like any NaN); centre cells matching `excludes` are copied.
-template <typename T> struct FocalMeanOp {
+template <typename T, typename TOUT = T> struct FocalMeanOp {
     using in_t = T;
-    using out_t = T;
+    using out_t = TOUT;
     static constexpr int kOutputs = 1;
     static constexpr int kMaxEx = 8;
     struct Params {
@@ -256,7 +256,7 @@ template <typename T> struct FocalMeanOp {
 #pragma unroll
         for (int i = 0; i < 4; ++i) s2[i] = s1[i] = 0.0, c2[i] = c1[i] = 0, ctr[i] = (T)0;
     }
-    __device__ __forceinline__ void step(const Row6<T> &row, Vec4<T> (&out)[1]) {
+    __device__ __forceinline__ void step(const Row6<T> &row, Vec4<TOUT> (&out)[1]) {
         double f[6];
         int m[6];
         T w[6];
@@ -278,8 +278,8 @@ template <typename T> struct FocalMeanOp {
             const T c = ctr[i];
             bool excl = (p.ex_nan != 0) && !(c == c);
             for (int k = 0; k < p.n_ex; ++k) excl = excl || ((double)c == p.ex[k]);
-            const T mean = (T)div_count9(sum, cnt);
-            out[0].v[i] = excl ? c : mean;
+            const TOUT mean = (TOUT)div_count9(sum, cnt);
+            out[0].v[i] = excl ? (TOUT)c : mean;
             s2[i] = s1[i]; s1[i] = hs;
             c2[i] = c1[i]; c1[i] = hc;
         }

@@ -54,7 +54,11 @@ def _stat_of(func):
 
 # ----------------------------------------------------------------------------- mean
 def _mean_numpy(data, excludes):
-    """One pass on a host float64 raster (replaces focal.py:44 `_mean_numpy`)."""
+    """One pass on a host raster, float64 result (replaces focal.py:44 `_mean_numpy` after the
+    `astype(float)` of focal.py:257; a float32 raster is widened inside the kernel)."""
+    if data.dtype == np.float32:
+        return run_stencil_host("focal_mean_f32_f64", data, aux=tuple(excludes), out_dtype=np.float64,
+                                in_dtype=np.float32)
     return run_stencil_host("focal_mean_f64", data, aux=tuple(excludes), out_dtype=np.float64,
                             in_dtype=np.float64)
 
