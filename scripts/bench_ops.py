@@ -1,0 +1,99 @@
+"""Per-operator device-resident throughput table (Mcells/s, GB/s of algorithmic bytes, fraction
+of the measured HBM peak) for every kernel on the hot path.  Not the driver's bench (bench.py);
+used to fill profiles/ops_rNN.json and the table in DESIGN.md."""
+import ctypes, json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import xrspatial_b200 as xb
+from xrspatial_b200 import _lib, focal
+from xrspatial_b200.convolution import convolve_2d
+
+side = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+peak = 6569.6
+try:
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+
+
+def synth(seed, lo, hi, h=side, w=side):
+    t = torch.empty((h, w), dtype=torch.float32, device="cuda")
+    _lib.call("xrs_synth_terrain_f32", ctypes.c_void_p(t.data_ptr()), w * 4, h, w, 0, 0, seed, lo, hi,
+              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    return t
+
+
+def timeit(fn, n=reps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+    ev[0].record()
+    for i in range(n):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    return float(np.median([ev[i].elapsed_time(ev[i + 1]) for i in range(n)]))
+
+
+dem = synth(1235, 0.0, 4000.0)
+agg = xb.DataArray(dem, dims=("y", "x"), attrs={"res": (30.0, 30.0)})
+cells = side * side
+rows = []
+
+
+def add(name, ms, bytes_per_cell, ncells=cells, note=""):
+    gbs = ncells * bytes_per_cell / (ms * 1e-3) / 1e9
+    rows.append(dict(op=name, ms=ms, mcells_s=ncells / (ms * 1e-3) / 1e6, alg_bytes_per_cell=bytes_per_cell,
+                     gbs=gbs, frac_of_measured_hbm=gbs / peak, note=note))
+    print("%-28s %9.3f ms %12.0f Mcells/s %8.0f GB/s  %.3f" % (name, ms, rows[-1]["mcells_s"], gbs, gbs / peak), flush=True)
+
+
+add("slope", timeit(lambda: xb.slope(agg)), 8)
+add("aspect", timeit(lambda: xb.aspect(agg)), 8)
+add("curvature", timeit(lambda: xb.curvature(agg)), 8)
+add("hillshade", timeit(lambda: xb.hillshade(agg)), 8)
+add("focal.mean f32", timeit(lambda: xb.mean(agg)), 8)
+add("surface suite (4 outputs)", timeit(lambda: xb.surface_suite(agg)), 20)
+add("suite slope+aspect+curvature", timeit(lambda: xb.surface_suite(agg, products=("slope", "aspect", "curvature"))), 16)
+d64 = dem[: side // 2].to(torch.float64)
+a64 = xb.DataArray(d64, dims=("y", "x"))
+add("focal.mean f64", timeit(lambda: xb.mean(a64)), 16, ncells=d64.numel())
+del d64, a64
+for k in (3, 9, 25):
+    kern = np.ones((k, k)) / (k * k)
+    sub = dem if k == 3 else dem[: side // (2 if k == 9 else 8)]
+    add("convolve_2d k=%d" % k, timeit(lambda: convolve_2d(sub, kern), n=max(3, reps // 2)), 8, ncells=sub.numel(),
+        note="f64 accumulate; bound = FP64 FMA rate for k>=5")
+k5 = np.ones((5, 5))
+sub = dem[: side // 4]
+sagg = xb.DataArray(sub, dims=("y", "x"))
+add("focal_stats mean 5x5", timeit(lambda: focal.apply(sagg, k5), n=3), 8, ncells=sub.numel())
+nir, red, blue = synth(2001, 0.02, 0.6), synth(2002, 0.02, 0.6), synth(2003, 0.02, 0.6)
+A = lambda t: xb.DataArray(t, dims=("y", "x"))  # noqa: E731
+add("ndvi", timeit(lambda: xb.ndvi(A(nir), A(red))), 12)
+add("savi", timeit(lambda: xb.savi(A(nir), A(red))), 12)
+add("evi", timeit(lambda: xb.evi(A(nir), A(red), A(blue))), 16)
+del nir, red, blue
+yy = torch.arange(side, device="cuda", dtype=torch.int32)[:, None] // (side // 32)
+xx = torch.arange(side, device="cuda", dtype=torch.int32)[None, :] // (side // 32)
+zones = (yy * 32 + xx).contiguous()
+zagg = A(zones)
+add("zonal.stats 1024 block zones", timeit(lambda: xb.zonal_stats(zagg, agg), n=3), 8,
+    note="includes zone-id discovery (min/max + presence pass) and host finalisation")
+ids = list(range(1024))
+from xrspatial_b200 import zonal as Z  # noqa: E402
+zt, vt = zones, dem
+sel = np.arange(1024, dtype=np.int32)
+add("zonal partials kernel only", timeit(lambda: Z.zonal_partials(zt, vt, sel)), 8,
+    note="xrs_zonal_partials_ex + tiny D2H of the partials")
+hz = ((torch.arange(side, device="cuda", dtype=torch.int64)[:, None] * 7919 +
+       torch.arange(side, device="cuda", dtype=torch.int64)[None, :] * 104729) % 1024).to(torch.int32)
+add("zonal partials scattered zones", timeit(lambda: Z.zonal_partials(hz, vt, sel), n=3), 8,
+    note="worst case: zone changes every cell")
+out = os.path.join(ROOT, "gpurun_out", "ops.json")
+os.makedirs(os.path.dirname(out), exist_ok=True)
+json.dump(dict(side=side, peak_gbs=peak, rows=rows), open(out, "w"), indent=1)

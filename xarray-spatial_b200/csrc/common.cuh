@@ -99,30 +99,30 @@ __device__ __forceinline__ float rcp_approx(float x) {
 
 // atan(a)/a on a in [0,1] as a degree-7 polynomial in z = a*a (minimax, rel err 1e-7;
 // 2.5e-7 evaluated in f32).  The reference evaluates np.arctan in f64 and rounds to f32;
-// the parity bar is 1e-5 relative.
-__device__ __forceinline__ float atan_poly01(float z) {
-    float p = -4.693183854e-03f;
-    p = fmaf(p, z, 2.425208207e-02f);
-    p = fmaf(p, z, -5.948595430e-02f);
-    p = fmaf(p, z, 9.914263125e-02f);
-    p = fmaf(p, z, -1.401947061e-01f);
-    p = fmaf(p, z, 1.996972220e-01f);
-    p = fmaf(p, z, -3.333199064e-01f);
-    p = fmaf(p, z, 9.999999010e-01f);
+// the parity bar is 1e-5 relative.  SCALE folds a unit conversion into the coefficients.
+template <int DEG> __device__ __forceinline__ float atan_poly01(float z) {
+    constexpr float k = DEG ? 57.29578f : 1.0f;  // slope.py:75 uses the literal 57.29578
+    float p = -4.693183854e-03f * k;
+    p = fmaf(p, z, 2.425208207e-02f * k);
+    p = fmaf(p, z, -5.948595430e-02f * k);
+    p = fmaf(p, z, 9.914263125e-02f * k);
+    p = fmaf(p, z, -1.401947061e-01f * k);
+    p = fmaf(p, z, 1.996972220e-01f * k);
+    p = fmaf(p, z, -3.333199064e-01f * k);
+    p = fmaf(p, z, 9.999999010e-01f * k);
     return p;
 }
 
 // degrees(atan(sqrt(p))) for p >= 0 (NaN propagates).  One MUFU.RSQ, no division:
-// for p > 1 uses atan(s) = pi/2 - atan(1/s) with 1/s = rsqrt(p).
+// for p > 1 uses atan(s) = pi/2 - atan(1/s) with 1/s = rsqrt(p).  p below 1e-30 (slope
+// below 6e-14 degrees) evaluates as p * 1e15, far under any tolerance.
 __device__ __forceinline__ float atan_sqrt_deg(float p) {
-    const float r = rsqrt_approx(p);
-    const bool big = p > 1.0f;
-    const float s = (p < 1e-30f) ? 0.0f : p * r;  // sqrt(p); NaN falls to p*r = NaN
+    const float r = rsqrt_approx(fmaxf(p, 1e-30f));
+    const float s = p * r;            // sqrt(p); NaN stays NaN
+    const bool big = p > 1.0f;        // false for NaN -> the NaN in `s` propagates
     const float a = big ? r : s;
-    const float z = big ? r * r : p;
-    const float t = a * atan_poly01(z);
-    const float rad = big ? (1.57079632679489662f - t) : t;
-    return rad * 57.29578f;
+    const float t = a * atan_poly01<1>(a * a);
+    return big ? (1.57079632679489662f * 57.29578f - t) : t;
 }
 
 // degrees(atan2(y, x)) in (-180, 180]; caller guarantees not both zero.  NaN propagates.
@@ -130,7 +130,7 @@ __device__ __forceinline__ float atan2_deg(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
     const float a = mn * rcp_approx(mx);
-    float r = a * atan_poly01(a * a);
+    float r = a * atan_poly01<0>(a * a);
     if (ay > ax) r = 1.57079632679489662f - r;
     if (x < 0.0f) r = 3.14159265358979323846f - r;
     if (y < 0.0f) r = -r;

@@ -43,9 +43,12 @@ template <typename T> struct Row6 {
     T l, c[4], r;
 };
 
-template <typename T> __device__ __forceinline__ Row6<T> load_row_smem(const T *row, int lane) {
+// `p` points at the lane's first cell inside a shared-memory row (16-byte aligned).  The left /
+// right neighbours are plain scalar loads (4-way bank conflicted, 8 extra wavefronts per
+// warp-row against a budget of ~44 cycles): cheaper in issue slots than shuffles plus
+// strip-edge fix-ups, and issue slots are what these kernels run out of.
+template <typename T> __device__ __forceinline__ Row6<T> load_row_smem(const T *p) {
     Row6<T> o;
-    const T *p = row + kPad + kLaneCells * lane;
     if constexpr (sizeof(T) == 4) {
         const float4 q = *reinterpret_cast<const float4 *>(p);
         o.c[0] = q.x; o.c[1] = q.y; o.c[2] = q.z; o.c[3] = q.w;
@@ -54,10 +57,8 @@ template <typename T> __device__ __forceinline__ Row6<T> load_row_smem(const T *
         const double2 q1 = *reinterpret_cast<const double2 *>(p + 2);
         o.c[0] = q0.x; o.c[1] = q0.y; o.c[2] = q1.x; o.c[3] = q1.y;
     }
-    o.l = shfl_up1(o.c[3]);
-    o.r = shfl_dn1(o.c[0]);
-    if (lane == 0) o.l = row[kPad - 1];
-    if (lane == 31) o.r = row[kPad + kStripW];
+    o.l = p[-1];
+    o.r = p[4];
     return o;
 }
 
@@ -90,6 +91,15 @@ template <typename TO> __device__ __forceinline__ void store4(TO *p, const Vec4<
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             if (i < nvalid) p[i] = v.v[i];
+    }
+}
+
+template <typename TO> __device__ __forceinline__ void store4v(TO *p, const Vec4<TO> &v) {
+    if constexpr (sizeof(TO) == 4) {
+        __stcs(reinterpret_cast<float4 *>(p), make_float4(v.v[0], v.v[1], v.v[2], v.v[3]));
+    } else {
+        __stcs(reinterpret_cast<double2 *>(p), make_double2(v.v[0], v.v[1]));
+        __stcs(reinterpret_cast<double2 *>(p + 2), make_double2(v.v[2], v.v[3]));
     }
 }
 
@@ -160,28 +170,34 @@ stencil3_tma_kernel(const __grid_constant__ CUtensorMap tmap,
 
         Op op(prm);
         const int64_t xl = x0 + kLaneCells * lane;
-        const int nvalid = (int)max((int64_t)0, min((int64_t)4, g.W - xl));
+        const bool lane_ok = xl < g.W;  // W % 4 == 0 on this path: a lane is all-in or all-out
+        const int seg_h = (int)(y1 - y0);
+        const T *lane_smem = ring + kPad + kLaneCells * lane;
+        // output pointers one row above the first emitted row (y0 - 2): advanced before every store
+        TO *optr[Op::kOutputs];
+#pragma unroll
+        for (int k = 0; k < Op::kOutputs; ++k) optr[k] = outs.p[k] + (y0 - 3) * outs.pitch_elems + xl;
 
         int stage = 0;
         for (int c = 0; c < n_chunks; ++c) {
             mbar_wait(&bars[stage], (phase >> stage) & 1u);
             phase ^= (1u << stage);
-            const T *buf = ring + stage * kStageElems;
-            const int64_t ybase = y0 - 1 + (int64_t)c * ROWS;
+            const T *buf = lane_smem + stage * kStageElems;
+            const int rel = c * ROWS - 2;  // output row (relative to y0) of the box's first row
+            // Straight-line over the ROWS rows of the box (no branch around the operator state
+            // update, so the rolling registers are renamed, not moved).  Rows whose output row
+            // falls outside [y0, y1) -- the two lead-in rows and the tail of the last chunk --
+            // still update the state; only their store is predicated off.
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
-                const int64_t yin = ybase + r;
-                if (yin <= y1) {  // warp-uniform
-                    const Row6<T> row = load_row_smem<T>(buf + r * kBoxW, lane);
-                    Vec4<TO> o[Op::kOutputs];
-                    op.step(row, o);
-                    const int64_t yout = yin - 1;
-                    if (yout >= y0 && nvalid > 0) {
+                const Row6<T> row = load_row_smem<T>(buf + r * kBoxW);
+                Vec4<TO> o[Op::kOutputs];
+                op.step(row, o);
+                const bool st = lane_ok && (unsigned)(rel + r) < (unsigned)seg_h;
 #pragma unroll
-                        for (int k = 0; k < Op::kOutputs; ++k)
-                            if (outs.p[k] != nullptr)
-                                store4<TO>(outs.p[k] + yout * outs.pitch_elems + xl, o[k], true, nvalid);
-                    }
+                for (int k = 0; k < Op::kOutputs; ++k) {
+                    optr[k] += outs.pitch_elems;
+                    if (st && (Op::kOutputs == 1 || outs.p[k] != nullptr)) store4v<TO>(optr[k], o[k]);
                 }
             }
             __syncwarp();  // every lane is done reading this stage

@@ -11,6 +11,14 @@ using namespace xrs;
 constexpr int kRowsF32 = 4, kStagesF32 = 4;
 constexpr int kRowsF64 = 2, kStagesF64 = 4;
 
+static SlopeOp::Params slope_params(double cellsize_x, double cellsize_y) {
+    const double kx = 1.0 / (8.0 * cellsize_x), ky = 1.0 / (8.0 * cellsize_y);
+    SlopeOp::Params p;
+    p.rxy = kx / ky;
+    p.ky2 = (float)(ky * ky);
+    return p;
+}
+
 static HillshadeOp::Params hillshade_params(double azimuth, double angle_altitude) {
     // hillshade.py:23-27: azimuth = 360 - azimuth; rad conversions in Python float (f64)
     const double az = 360.0 - azimuth;
@@ -27,10 +35,12 @@ static HillshadeOp::Params hillshade_params(double azimuth, double angle_altitud
 template <typename T, typename TOUT, int ROWS, int STAGES>
 static int focal_mean_impl(const T *in, int64_t in_pitch, TOUT *out, int64_t out_pitch, int64_t H, int64_t W,
                            const double *excludes, int n_ex, xrs_stream_t s) {
-    using Op = FocalMeanOp<T, TOUT>;
+    using Op = FocalMeanOp<T, TOUT, false>;
+    using OpEx = FocalMeanOp<T, TOUT, true>;
+    static_assert(sizeof(typename Op::Params) == sizeof(typename OpEx::Params), "same parameter block");
     XRS_REQUIRE(n_ex >= 0 && n_ex <= Op::kMaxEx, "at most 8 exclude values are supported");
     XRS_REQUIRE(n_ex == 0 || excludes != nullptr, "excludes is NULL");
-    typename Op::Params p;
+    typename OpEx::Params p;
     p.n_ex = 0;
     p.ex_nan = 0;
     for (int i = 0; i < Op::kMaxEx; ++i) p.ex[i] = 0.0;
@@ -39,16 +49,17 @@ static int focal_mean_impl(const T *in, int64_t in_pitch, TOUT *out, int64_t out
         else p.ex[p.n_ex++] = excludes[i];
     }
     TOUT *outs[1] = {out};
-    return launch_stencil3<Op, ROWS, STAGES>(in, in_pitch, p, outs, out_pitch, H, W, (cudaStream_t)s);
+    if (p.n_ex > 0 || !p.ex_nan) return launch_stencil3<OpEx, ROWS, STAGES>(in, in_pitch, p, outs, out_pitch, H, W, (cudaStream_t)s);
+    typename Op::Params q;
+    memcpy(&q, &p, sizeof(q));
+    return launch_stencil3<Op, ROWS, STAGES>(in, in_pitch, q, outs, out_pitch, H, W, (cudaStream_t)s);
 }
 
 extern "C" {
 
 int xrs_slope_f32(const float *in, int64_t in_pitch, float *out, int64_t out_pitch, int64_t H, int64_t W,
                   double cellsize_x, double cellsize_y, xrs_stream_t s) {
-    SlopeOp::Params p;
-    p.kx = 1.0 / (8.0 * cellsize_x);
-    p.ky = 1.0 / (8.0 * cellsize_y);
+    const SlopeOp::Params p = slope_params(cellsize_x, cellsize_y);
     float *outs[1] = {out};
     return launch_stencil3<SlopeOp, kRowsF32, kStagesF32>(in, in_pitch, p, outs, out_pitch, H, W,
                                                           (cudaStream_t)s);
@@ -84,8 +95,7 @@ int xrs_surface_suite_f32(const float *in, int64_t in_pitch, float *slope_out, f
                           int64_t W, double cellsize_x, double cellsize_y, double azimuth,
                           double angle_altitude, xrs_stream_t s) {
     SuiteOp::Params p;
-    p.slope.kx = 1.0 / (8.0 * cellsize_x);
-    p.slope.ky = 1.0 / (8.0 * cellsize_y);
+    p.slope = slope_params(cellsize_x, cellsize_y);
     const double cs = (cellsize_x + cellsize_y) / 2;  // curvature.py:234
     p.curv.k = 100.0 / (cs * cs);
     p.hill = hillshade_params(azimuth, angle_altitude);

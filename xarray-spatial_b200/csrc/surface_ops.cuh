@@ -37,7 +37,8 @@ struct SlopeOp {
     using out_t = float;
     static constexpr int kOutputs = 1;
     struct Params {
-        double kx, ky;  // 1/(8*cellsize_x), 1/(8*cellsize_y)
+        double rxy;  // (1/(8 csx)) / (1/(8 csy)) = csy / csx
+        float ky2;   // (1/(8 csy))^2
     };
     const Params &p;
     HornRow m2, m1;  // rows y-2, y-1 relative to the row being pushed
@@ -45,10 +46,12 @@ struct SlopeOp {
 #pragma unroll
         for (int i = 0; i < 4; ++i) m2.D[i] = m2.S[i] = m1.D[i] = m1.S[i] = 0.0;
     }
+    // p = dz_dx^2 + dz_dy^2 = ky^2 ((X kx/ky)^2 + Y^2): X, Y are exact in f64, the sum of
+    // squares is formed in f64 and only then rounded to f32 (the result needs f32 accuracy).
     static __device__ __forceinline__ float eval(double X, double Y, const Params &p) {
-        const double dx = X * p.kx, dy = Y * p.ky;
-        const float pf = (float)fma(dx, dx, dy * dy);
-        return atan_sqrt_deg(pf);
+        const double xs = X * p.rxy;
+        const float q = (float)fma(xs, xs, Y * Y);
+        return atan_sqrt_deg(q * p.ky2);
     }
     __device__ __forceinline__ void step(const Row6<float> &row, Vec4<float> (&out)[1]) {
         const HornRow n = horn_row(row);
@@ -225,20 +228,27 @@ struct SuiteOp {
 // sum / cnt for cnt in 0..9 without a f64 division: multiply by a tabulated reciprocal and
 // apply one FMA correction step (the quotient is then correctly rounded except in rare
 // halfway cases; 0/0 gives NaN like np.divide).
+// entry 0 is NaN: an empty window has s = 0 and 0 * NaN = NaN, like np.divide(0., 0)
 __constant__ double kRcp9[10] = {
-    0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9};
-__device__ __forceinline__ double div_count9(double s, int cnt) {
-    if (cnt == 0) return nan_of<double>();
-    const double r = kRcp9[cnt], n = (double)cnt;
+    __builtin_nan(""), 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9};
+__constant__ double kCnt9[10] = {0.0, 1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0, 9.0};
+template <typename TOUT> __device__ __forceinline__ TOUT div_count9(double s, int cnt) {
+    const double r = kRcp9[cnt];
     const double q = s * r;
-    const double e = fma(-q, n, s);
-    return fma(e, r, q);
+    if constexpr (sizeof(TOUT) == 4) {
+        // float32 result: s * (1/n) is within one f64 ulp of s / n, so the f32 rounding agrees
+        // with the oracle except when s / n sits within 1e-16 of an f32 rounding boundary
+        return (float)q;
+    } else {
+        const double e = fma(-q, kCnt9[cnt], s);
+        return fma(e, r, q);
+    }
 }
 
 // ------------------------------------------------------------------ focal.mean (focal.py:44-67)
 // 3x3 NaN-skipping mean over the window clamped to the raster (out-of-raster cells arrive
 // as NaN and are skipped like any NaN); centre cells matching `excludes` are copied.
-template <typename T, typename TOUT = T> struct FocalMeanOp {
+template <typename T, typename TOUT = T, bool HAS_EX = false> struct FocalMeanOp {
     using in_t = T;
     using out_t = TOUT;
     static constexpr int kOutputs = 1;
@@ -266,7 +276,7 @@ template <typename T, typename TOUT = T> struct FocalMeanOp {
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
             const bool ok = (w[i] == w[i]);
-            f[i] = ok ? (double)w[i] : 0.0;
+            f[i] = (double)(ok ? w[i] : (T)0);
             m[i] = ok ? 1 : 0;
         }
 #pragma unroll
@@ -276,9 +286,14 @@ template <typename T, typename TOUT = T> struct FocalMeanOp {
             const double sum = (s2[i] + s1[i]) + hs;
             const int cnt = c2[i] + c1[i] + hc;
             const T c = ctr[i];
-            bool excl = (p.ex_nan != 0) && !(c == c);
-            for (int k = 0; k < p.n_ex; ++k) excl = excl || ((double)c == p.ex[k]);
-            const TOUT mean = (TOUT)div_count9(sum, cnt);
+            bool excl;
+            if constexpr (HAS_EX) {  // arbitrary exclude lists: rare, kept off the default path
+                excl = (p.ex_nan != 0) && !(c == c);
+                for (int k = 0; k < p.n_ex; ++k) excl = excl || ((double)c == p.ex[k]);
+            } else {  // the default excludes=[nan]
+                excl = !(c == c);
+            }
+            const TOUT mean = div_count9<TOUT>(sum, cnt);
             out[0].v[i] = excl ? (TOUT)c : mean;
             s2[i] = s1[i]; s1[i] = hs;
             c2[i] = c1[i]; c1[i] = hc;
