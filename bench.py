@@ -119,6 +119,14 @@ def cpu_steps(sample, threads, steps, warmup):
     return times
 
 
+def host_threads():
+    """All host cores this process may use (torchrun pins OMP_NUM_THREADS=1, so ask the OS)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def host_sample(rows, cols, seed=1234):
     """Cheap host-side DEM for the CPU arm when no GPU generated one (same statistics)."""
     rng = np.random.default_rng(seed)
@@ -136,7 +144,7 @@ def run_reference_arm(args):
         return
     import oracle
     oracle.build()
-    threads = oracle.max_threads()
+    threads = host_threads()
     rows = cols = args.cpu_sample
     sample = host_sample(rows, cols)
     times = cpu_steps(sample, threads, args.steps, args.warmup)
@@ -266,8 +274,8 @@ def run_gpu_arm(args):
     e2e = None
     cpu = None
     if rank == 0 and n_gpus == 1:
-        e2e = run_e2e(xb, stripes, H, W, attrs, args)
-        cpu = run_cpu_baseline(stripes, args)
+        e2e = None if args.skip_host else run_e2e(xb, stripes, H, W, attrs, args)
+        cpu = None if args.skip_host else run_cpu_baseline(stripes, args)
     elif rank == 0:
         e2e = {"value": None, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "note": "host-buffer path is measured at N=1 (it drives one GPU per call)"}
@@ -339,7 +347,7 @@ def run_cpu_baseline(stripes, args):
     oracle.build()
     n = min(args.cpu_sample, stripes.h, stripes.W)
     sample = stripes.interior[:n, :n].contiguous().cpu().numpy()
-    threads = oracle.max_threads()
+    threads = host_threads()
     t_all = float(np.mean(cpu_steps(sample, threads, 2, 1)))
     t_one = float(np.mean(cpu_steps(sample[: max(256, n // 4)], 1, 1, 1)))
     cells = 3.0 * n * n
@@ -359,6 +367,8 @@ def main():
     ap.add_argument("--raster", type=int, default=0, help="raster side (default 32768 at N=1, 65536 at N>1)")
     ap.add_argument("--cpu-sample", type=int, default=8192, help="side of the CPU-arm sample window")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--skip-host", action="store_true",
+                    help="profiling runs only: skip the e2e (host-buffer) and CPU-baseline legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -151,12 +151,30 @@ int xrs_zonal_partials(const void *values, int values_dtype, const void *zones,
                        xrs_stream_t s);
 /* same, with a hint for integer zone rasters whose ids all lie in
  * [lut_base, lut_base + 8192): use_lut != 0 replaces the binary search of zone_ids by a
- * direct shared-memory table. */
+ * direct shared-memory table.  row_len = raster row length (n = rows * row_len), see
+ * xrs_zonal_hash_accumulate. */
 int xrs_zonal_partials_ex(const void *values, int values_dtype, const void *zones,
                           int zones_dtype, int64_t n, const double *zone_ids, int nz,
                           const double *pivot, int has_nodata, double nodata, int use_lut,
-                          int64_t lut_base, int64_t *count, double *sum, double *sumsq,
-                          double *vmin, double *vmax, xrs_stream_t s);
+                          int64_t lut_base, int64_t row_len, int64_t *count, double *sum,
+                          double *sumsq, double *vmin, double *vmax, xrs_stream_t s);
+
+/* Single-pass variant that DISCOVERS the zone ids: group-by aggregation into an open-addressing
+ * hash table of `cap` slots (power of two >= 1024; device arrays keys/count/s1/s2/vmin/vmax of
+ * `cap` entries, initialised by xrs_zonal_hash_init).  keys[slot] is the zone id (int64 for
+ * integer zones, the bit pattern of the float64 value for float zones; INT64_MIN = empty),
+ * s1/s2 are sums of (v - pivot) and (v - pivot)^2.  Every finite zone value present in the
+ * raster gets a slot, also when none of its cells is valid (count 0).  *overflow (device
+ * int) is set when the raster holds more than `cap` distinct zones.  row_len is the raster's
+ * row length (n = rows * row_len): the scan walks down 128-column strips so that runs of equal
+ * zone ids stay long. */
+int xrs_zonal_hash_init(int64_t *keys, int64_t *count, double *s1, double *s2, double *vmin,
+                        double *vmax, int cap, int *overflow, xrs_stream_t s);
+int xrs_zonal_hash_accumulate(const void *values, int values_dtype, const void *zones,
+                              int zones_dtype, int64_t n, int64_t row_len, double pivot, int has_nodata,
+                              double nodata, int64_t *keys, int64_t *count, double *s1,
+                              double *s2, double *vmin, double *vmax, int cap, int *overflow,
+                              xrs_stream_t s);
 
 /* ------------------------------------------------------------------ host-buffer (end-to-end)
  * Same operators on HOST rasters: the library stripes the raster over rows, and overlaps

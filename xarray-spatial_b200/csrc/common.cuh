@@ -125,17 +125,26 @@ __device__ __forceinline__ float atan_sqrt_deg(float p) {
     return big ? (1.57079632679489662f * 57.29578f - t) : t;
 }
 
-// degrees(atan2(y, x)) in (-180, 180]; caller guarantees not both zero.  NaN propagates.
-__device__ __forceinline__ float atan2_deg(float y, float x) {
-    const float ax = fabsf(x), ay = fabsf(y);
-    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    const float a = mn * rcp_approx(mx);
-    float r = a * atan_poly01<0>(a * a);
-    if (ay > ax) r = 1.57079632679489662f - r;
-    if (x < 0.0f) r = 3.14159265358979323846f - r;
-    if (y < 0.0f) r = -r;
-    r *= 57.29577951308232f;
-    return (x != x || y != y) ? __int_as_float(0x7fc00000) : r;
+// Compass aspect from the exact Horn sums X = 8 dz_dx, Y = 8 dz_dy (aspect.py:74-88):
+// the reference's (90 - atan2(Y, -X) deg) folded to [0, 360) is atan2(u, v) with u = -X, v = Y,
+// folded to [0, 360).  One octant reduction (ratio of the smaller to the larger magnitude,
+// one MUFU.RCP, degree-7 polynomial already scaled to degrees), then compass = K + sigma*base
+// with (K, sigma) picked per octant.  Evaluating the compass angle directly keeps full
+// relative accuracy near 0 degrees, where `90 - theta` would cancel.  Flat cells (both
+// sums zero) give -1; NaN propagates (selects, not fmin/fmax, pick the operands).
+__device__ __forceinline__ float compass_deg(float u, float v) {
+    const float au = fabsf(u), av = fabsf(v);
+    const bool swap = au > av;                // closer to the +-u axis (east / west)
+    const float mx = swap ? au : av, mn = swap ? av : au;
+    const float t = mn * rcp_approx(mx);
+    const float base = t * atan_poly01<1>(t * t);                 // [0, 45] degrees
+    // sigma = sign(u) * sign(v), negated in the swapped octants: flip base's sign bit
+    const unsigned sgn = ((__float_as_uint(u) ^ __float_as_uint(v)) & 0x80000000u) ^ (swap ? 0x80000000u : 0u);
+    const float sb = __uint_as_float(__float_as_uint(base) ^ sgn);
+    const float k_ns = (v > 0.0f) ? ((u < 0.0f) ? 360.0f : 0.0f) : 180.0f;
+    const float k_ew = (u > 0.0f) ? 90.0f : 270.0f;
+    const float r = (swap ? k_ew : k_ns) + sb;
+    return (mx == 0.0f) ? -1.0f : r;
 }
 
 }  // namespace xrs

@@ -282,6 +282,9 @@ static bool tile_geom(TileGeom &g, CUtensorMap *tmap, const float *in, int64_t i
 
 using namespace xrs;
 
+int xrs_conv3_strip(const float *in, int64_t in_pitch, float *out, int64_t out_pitch, int64_t H, int64_t W,
+                    const double *kernel, cudaStream_t s);  // surface.cu
+
 extern "C" {
 
 int xrs_convolve2d_f32(const float *in, int64_t in_pitch, float *out, int64_t out_pitch, int64_t H, int64_t W,
@@ -289,6 +292,7 @@ int xrs_convolve2d_f32(const float *in, int64_t in_pitch, float *out, int64_t ou
     if (H <= 0 || W <= 0) return XRS_OK;
     const int rc = check_common(in, in_pitch, out, out_pitch, H, W, kernel, kh, kw);
     if (rc) return rc;
+    if (kh == 3 && kw == 3) return xrs_conv3_strip(in, in_pitch, out, out_pitch, H, W, kernel, (cudaStream_t)s);
     static thread_local ConvWeights cw;
     for (int i = 0; i < kh * kw; ++i) cw.w[i] = kernel[i];
     TileGeom g;

@@ -32,6 +32,15 @@ static HillshadeOp::Params hillshade_params(double azimuth, double angle_altitud
     return p;
 }
 
+// 3x3 kernels of convolve_2d take the warp-strip path (called from conv.cu)
+int xrs_conv3_strip(const float *in, int64_t in_pitch, float *out, int64_t out_pitch, int64_t H, int64_t W,
+                    const double *kernel, cudaStream_t s) {
+    Conv3Op::Params p;
+    for (int i = 0; i < 9; ++i) p.w[i] = kernel[i];
+    float *outs[1] = {out};
+    return launch_stencil3<Conv3Op, kRowsF32, kStagesF32>(in, in_pitch, p, outs, out_pitch, H, W, s);
+}
+
 template <typename T, typename TOUT, int ROWS, int STAGES>
 static int focal_mean_impl(const T *in, int64_t in_pitch, TOUT *out, int64_t out_pitch, int64_t H, int64_t W,
                            const double *excludes, int n_ex, xrs_stream_t s) {

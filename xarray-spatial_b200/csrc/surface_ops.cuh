@@ -80,13 +80,11 @@ struct AspectOp {
 #pragma unroll
         for (int i = 0; i < 4; ++i) m2.D[i] = m2.S[i] = m1.D[i] = m1.S[i] = 0.0;
     }
-    // X = 8*dz_dx, Y = 8*dz_dy (exact).  compass = (90 - atan2(Y, -X)) mod 360, which is
-    // atan2(-X, Y) folded into [0, 360): evaluating it directly keeps full relative
-    // accuracy near 0 degrees, where `90 - theta` would cancel.
+    // X = 8*dz_dx, Y = 8*dz_dy, exact in f64; rounding them to f32 (6e-8) before the octant
+    // reduction is far inside the 1e-5 bar, and (float)X == 0 iff X == 0 for any raster whose
+    // cells are not denormal, so the flat (-1) mask is the reference's bit for bit.
     static __device__ __forceinline__ float eval(double X, double Y) {
-        if (X == 0.0 && Y == 0.0) return -1.0f;
-        const float a = atan2_deg((float)(-X), (float)Y);
-        return a < 0.0f ? a + 360.0f : a;
+        return compass_deg((float)(-X), (float)Y);
     }
     __device__ __forceinline__ void step(const Row6<float> &row, Vec4<float> (&out)[1]) {
         const HornRow n = horn_row(row);
@@ -222,6 +220,44 @@ struct SuiteOp {
 #pragma unroll
         for (int i = 0; i < 4; ++i) n2[i] = r1.c[i];
         r1 = row;
+    }
+};
+
+// ------------------------------------------------------------------ 3x3 convolution (convolution.py:285-313)
+// k = 3 runs on the warp-strip skeleton (HBM-bound) instead of the k x k tile kernel: float64
+// accumulation in the reference's row-major tap order, NaN ring from the TMA fill.
+struct Conv3Op {
+    using in_t = float;
+    using out_t = float;
+    static constexpr int kOutputs = 1;
+    struct Params {
+        double w[9];
+    };
+    const Params &p;
+    double r2[6], r1[6];  // rows y-2, y-1 widened to f64: left, 4 cells, right
+    __device__ explicit Conv3Op(const Params &pp) : p(pp) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) r2[i] = r1[i] = 0.0;
+    }
+    __device__ __forceinline__ void step(const Row6<float> &row, Vec4<float> (&out)[1]) {
+        double n[6];
+        n[0] = (double)row.l;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) n[i + 1] = (double)row.c[i];
+        n[5] = (double)row.r;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) acc = fma(p.w[kx], r2[i + kx], acc);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) acc = fma(p.w[3 + kx], r1[i + kx], acc);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) acc = fma(p.w[6 + kx], n[i + kx], acc);
+            out[0].v[i] = (float)acc;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) r2[i] = r1[i], r1[i] = n[i];
     }
 };
 

@@ -51,6 +51,7 @@ struct ZonalArgs {
     const void *values;
     const void *zones;
     int64_t n;
+    int64_t W;               // row length (n = H * W): the scan walks down 128-column strips
     const double *zone_ids;  // sorted unique, device
     const double *pivot;     // device, nz
     int nz;
@@ -166,34 +167,59 @@ __global__ void __launch_bounds__(kZonalThreads) zonal_kernel(const __grid_const
         return -1;
     };
 
-    const int64_t nquads = (a.n + 3) >> 2;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads;
-         q += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i0 = q << 2;
-        const Quad<VT> v = load_quad<VT>(values, i0, a.n, v_al);
-        const Quad<ZT> z = load_quad<ZT>(zones, i0, a.n, z_al);
+    // column-strip traversal (see zonal_hash.cu): a warp walks down a 128-column strip, so a
+    // lane's run of equal zone ids is long and flushes are rare
+    const int lane = threadIdx.x & 31;
+    const int64_t H = a.n / a.W;
+    const int64_t n_strips = (a.W + 127) / 128;
+    constexpr int kSegRows = 256, kUnroll = 4;
+    const int64_t n_segs = (H + kSegRows - 1) / kSegRows;
+    const int64_t n_tasks = n_strips * n_segs;
+    const int64_t warps_total = (int64_t)gridDim.x * (kZonalThreads / 32);
+    const bool row_vec = v_al && z_al && (a.W % 4 == 0);
+    for (int64_t task = (int64_t)blockIdx.x * (kZonalThreads / 32) + (threadIdx.x >> 5); task < n_tasks;
+         task += warps_total) {
+        const int64_t seg = task / n_strips, strip = task % n_strips;
+        const int64_t x = strip * 128 + 4 * lane;
+        const int64_t y0 = seg * kSegRows, y1 = min(y0 + (int64_t)kSegRows, H);
+        const int nv = (int)max((int64_t)0, min((int64_t)4, a.W - x));  // 0: lane past the right edge
+        for (int64_t y = y0; y < y1; y += kUnroll) {
+            Quad<VT> vq[kUnroll];
+            Quad<ZT> zq[kUnroll];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i0 + k >= a.n) break;
-            const ZT zk = z.v[k];
-            if (!have || !(zk == cur_z)) {
-                flush();
-                cur = lookup(zk);
-                cur_z = zk;
-                have = (zk == zk);
-                cur_p = cur >= 0 ? piv[cur] : 0.0;
+            for (int u = 0; u < kUnroll; ++u) {
+                const int64_t i0 = (y + u) * a.W + x;
+                const int nvu = (y + u < y1) ? nv : 0;
+                vq[u] = load_quad<VT>(values, i0, i0 + nvu, row_vec);
+                zq[u] = load_quad<ZT>(zones, i0, i0 + nvu, row_vec);
             }
-            if (cur < 0) continue;
-            const double x = (double)v.v[k];
-            // finite and != nodata (zonal.py:159)
-            if (!(fabs(x) <= 1.7976931348623157e308)) continue;
-            if (a.has_nodata && x == a.nodata) continue;
-            const double d = x - cur_p;
-            acc.s1 += d;
-            acc.s2 = fma(d, d, acc.s2);
-            acc.mn = fmin(acc.mn, x);
-            acc.mx = fmax(acc.mx, x);
-            acc.cnt += 1u;
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int nvu = (y + u < y1) ? nv : 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool live = k < nvu;
+                    const ZT zk = zq[u].v[k];
+                    if (live && (!have || !(zk == cur_z))) {
+                        flush();
+                        cur = lookup(zk);
+                        cur_z = zk;
+                        have = (zk == zk);
+                        cur_p = cur >= 0 ? piv[cur] : 0.0;
+                    }
+                    const double xv = (double)vq[u].v[k];
+                    // finite and != nodata (zonal.py:159); branch-free accumulate
+                    const bool ok = live && cur >= 0 && (fabs(xv) <= 1.7976931348623157e308) &&
+                                    !(a.has_nodata && xv == a.nodata);
+                    const double d = ok ? xv - cur_p : 0.0;
+                    acc.s1 += d;
+                    acc.s2 = fma(d, d, acc.s2);
+                    acc.mn = ok ? fmin(acc.mn, xv) : acc.mn;
+                    acc.mx = ok ? fmax(acc.mx, xv) : acc.mx;
+                    acc.cnt += ok ? 1u : 0u;
+                }
+                __syncwarp();  // lanes that took the (rare) flush path rejoin the warp here
+            }
         }
     }
     flush();
@@ -231,7 +257,8 @@ template <typename VT, typename ZT> static int launch_zonal(const ZonalArgs &a, 
     if (per_sm > 8) per_sm = 8;
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)sm_count() * per_sm;
-    const int64_t need = ((a.n + 3) / 4 + kZonalThreads - 1) / kZonalThreads;
+    const int64_t n_tasks = ((a.W + 127) / 128) * ((a.n / a.W + 255) / 256);
+    const int64_t need = (n_tasks + kZonalThreads / 32 - 1) / (kZonalThreads / 32);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, kZonalThreads, smem, s>>>(a);
@@ -260,15 +287,16 @@ int xrs_zonal_init(int64_t *count, double *sum, double *sumsq, double *vmin, dou
 // xrs_zonal_partials is the portable entry point (binary search).
 int xrs_zonal_partials_ex(const void *values, int values_dtype, const void *zones, int zones_dtype, int64_t n,
                           const double *zone_ids, int nz, const double *pivot, int has_nodata, double nodata,
-                          int use_lut, int64_t lut_base, int64_t *count, double *sum, double *sumsq,
-                          double *vmin, double *vmax, xrs_stream_t s) {
+                          int use_lut, int64_t lut_base, int64_t row_len, int64_t *count, double *sum,
+                          double *sumsq, double *vmin, double *vmax, xrs_stream_t s) {
     if (n <= 0 || nz <= 0) return XRS_OK;
+    XRS_REQUIRE(row_len >= 1 && n % row_len == 0, "n must be a multiple of row_len");
     XRS_REQUIRE(values && zones && zone_ids && pivot && count && sum && sumsq && vmin && vmax, "NULL pointer");
     XRS_REQUIRE(values_dtype == XRS_F32 || values_dtype == XRS_F64, "values must be float32 or float64");
     XRS_REQUIRE(zones_dtype >= XRS_F32 && zones_dtype <= XRS_I64, "unknown zones dtype");
     if (zones_dtype == XRS_F32 || zones_dtype == XRS_F64) use_lut = 0;
     ZonalArgs a;
-    a.values = values; a.zones = zones; a.n = n; a.zone_ids = zone_ids; a.pivot = pivot; a.nz = nz;
+    a.values = values; a.zones = zones; a.n = n; a.W = row_len; a.zone_ids = zone_ids; a.pivot = pivot; a.nz = nz;
     a.has_nodata = has_nodata; a.nodata = nodata; a.use_lut = use_lut; a.lut_base = lut_base;
     a.count = (long long *)count; a.sum = sum; a.sumsq = sumsq; a.vmin = vmin; a.vmax = vmax;
     cudaStream_t st = (cudaStream_t)s;
@@ -287,7 +315,7 @@ int xrs_zonal_partials(const void *values, int values_dtype, const void *zones, 
                        const double *zone_ids, int nz, const double *pivot, int has_nodata, double nodata,
                        int64_t *count, double *sum, double *sumsq, double *vmin, double *vmax, xrs_stream_t s) {
     return xrs_zonal_partials_ex(values, values_dtype, zones, zones_dtype, n, zone_ids, nz, pivot, has_nodata,
-                                 nodata, 0, 0, count, sum, sumsq, vmin, vmax, s);
+                                 nodata, 0, 0, n, count, sum, sumsq, vmin, vmax, s);
 }
 
 }  // extern "C"

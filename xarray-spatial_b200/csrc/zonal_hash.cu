@@ -1,0 +1,372 @@
+// zonal_hash.cu -- single-pass zonal.stats partials without knowing the zone ids in advance.
+//
+// zonal.py:280-332 discovers the ids with np.unique and sorts the raster by zone (argsort).
+// Here the ids are discovered BY the streaming pass itself: a group-by aggregation into an
+// open-addressing hash table keyed by the zone id.
+//   * every thread streams quads of 4 consecutive cells (128-bit loads, UNROLL quads in flight
+//     before any is consumed) and keeps a private accumulator for the run of equal zone ids it
+//     is in (count, sum and sum of squares about a global pivot in f64, min / max);
+//   * when the id changes the run is merged into a per-CTA shared-memory hash table
+//     (atomicCAS on the key, native shared-memory atomics on the accumulators);
+//   * at the end each CTA merges its table into the global table (same probing, global
+//     atomics).  Tables from several GPUs are merged by key on the host (a few KB).
+// 8 algorithmic bytes per cell (f32 values + i32 zones): HBM-bound.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace xrs {
+
+constexpr int kZhThreads = 256;
+constexpr int kZhLocalCap = 1024;       // per-CTA table slots (power of two)
+constexpr int kZhUnroll = 4;            // rows per lane in flight
+constexpr int kZhSegRows = 256;         // rows per task
+constexpr long long kZhEmpty = (long long)0x8000000000000000ULL;
+
+struct ZhArgs {
+    const void *values;
+    const void *zones;
+    int64_t n;
+    int64_t W;      // row length of the raster (n = H * W); walking DOWN columns keeps runs long
+    double pivot;
+    int has_nodata;
+    double nodata;
+    long long *keys;
+    unsigned long long *count;
+    double *s1, *s2, *vmin, *vmax;
+    int cap;  // global slots, power of two
+    int *overflow;
+};
+
+__device__ __forceinline__ unsigned zh_hash(long long key) {
+    return (unsigned)(((unsigned long long)key * 0x9E3779B97F4A7C15ULL) >> 32);
+}
+__device__ __forceinline__ void zh_atomic_min(double *addr, double v) {
+    unsigned long long *a = reinterpret_cast<unsigned long long *>(addr);
+    unsigned long long old = *a;
+    while (v < __longlong_as_double((long long)old)) {
+        const unsigned long long assumed = old;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+        if (old == assumed) break;
+    }
+}
+__device__ __forceinline__ void zh_atomic_max(double *addr, double v) {
+    unsigned long long *a = reinterpret_cast<unsigned long long *>(addr);
+    unsigned long long old = *a;
+    while (v > __longlong_as_double((long long)old)) {
+        const unsigned long long assumed = old;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+        if (old == assumed) break;
+    }
+}
+
+// find-or-insert `key`; returns the slot or -1 when `max_probe` slots were all taken by others
+__device__ __forceinline__ int zh_slot(long long *keys, int cap, long long key, int max_probe) {
+    unsigned s = zh_hash(key) & (unsigned)(cap - 1);
+    for (int p = 0; p < max_probe; ++p) {
+        const long long k = keys[s];
+        if (k == key) return (int)s;
+        if (k == kZhEmpty) {
+            const long long prev = (long long)atomicCAS(reinterpret_cast<unsigned long long *>(&keys[s]),
+                                                        (unsigned long long)kZhEmpty, (unsigned long long)key);
+            if (prev == kZhEmpty || prev == key) return (int)s;
+        }
+        s = (s + 1) & (unsigned)(cap - 1);
+    }
+    return -1;
+}
+
+template <typename ZT> __device__ __forceinline__ bool zh_key(ZT z, long long &key) {
+    if constexpr (sizeof(ZT) == 4 && ZT(0.5) == ZT(0)) {  // int32
+        key = (long long)z;
+        return true;
+    } else if constexpr (sizeof(ZT) == 8 && ZT(0.5) == ZT(0)) {  // int64
+        key = (long long)z;
+        return key != kZhEmpty;
+    } else {  // float / double zones: finite values only (zonal.py:290), -0.0 folded into +0.0
+        const double d = (double)z + 0.0;
+        if (!(fabs(d) <= 1.7976931348623157e308)) return false;
+        key = __double_as_longlong(d);
+        return true;
+    }
+}
+
+struct ZhRun {
+    double s1, s2;
+    float mnf, mxf;     // used for float values
+    double mnd, mxd;    // used for double values
+    unsigned cnt;
+};
+
+template <typename VT> __device__ __forceinline__ void zh_reset(ZhRun &r) {
+    r.s1 = r.s2 = 0.0;
+    r.cnt = 0u;
+    r.mnf = INFINITY; r.mxf = -INFINITY;
+    r.mnd = INFINITY; r.mxd = -INFINITY;
+}
+
+template <typename VT> __device__ __forceinline__ void zh_add(ZhRun &r, VT v, const ZhArgs &a) {
+    if constexpr (sizeof(VT) == 4) {
+        const bool ok = (fabsf(v) <= 3.402823466e38f) && !(a.has_nodata && (double)v == a.nodata);
+        if (ok) {
+            const double d = (double)v - a.pivot;
+            r.s1 += d;
+            r.s2 = fma(d, d, r.s2);
+            r.mnf = fminf(r.mnf, v);
+            r.mxf = fmaxf(r.mxf, v);
+            r.cnt += 1u;
+        }
+    } else {
+        const bool ok = (fabs(v) <= 1.7976931348623157e308) && !(a.has_nodata && v == a.nodata);
+        if (ok) {
+            const double d = v - a.pivot;
+            r.s1 += d;
+            r.s2 = fma(d, d, r.s2);
+            r.mnd = fmin(r.mnd, v);
+            r.mxd = fmax(r.mxd, v);
+            r.cnt += 1u;
+        }
+    }
+}
+
+template <typename T> struct ZhQuad { T v[4]; };
+template <typename T> __device__ __forceinline__ ZhQuad<T> zh_load(const T *p, int64_t i, int64_t n, bool al) {
+    ZhQuad<T> q;
+    if (al && i + 4 <= n) {
+        if constexpr (sizeof(T) == 4) {
+            const int4 r = __ldcs(reinterpret_cast<const int4 *>(p + i));
+            memcpy(&q.v[0], &r, 16);
+        } else {
+            const int4 r0 = __ldcs(reinterpret_cast<const int4 *>(p + i));
+            const int4 r1 = __ldcs(reinterpret_cast<const int4 *>(p + i + 2));
+            memcpy(&q.v[0], &r0, 16);
+            memcpy(&q.v[2], &r1, 16);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q.v[k] = (i + k < n) ? p[i + k] : T(0);
+    }
+    return q;
+}
+
+template <typename VT, typename ZT>
+__global__ void __launch_bounds__(kZhThreads) zonal_hash_kernel(const __grid_constant__ ZhArgs a) {
+    __shared__ long long s_keys[kZhLocalCap];
+    __shared__ double s_s1[kZhLocalCap], s_s2[kZhLocalCap], s_mn[kZhLocalCap], s_mx[kZhLocalCap];
+    __shared__ unsigned s_cnt[kZhLocalCap];
+    for (int i = threadIdx.x; i < kZhLocalCap; i += blockDim.x) {
+        s_keys[i] = kZhEmpty;
+        s_s1[i] = 0.0; s_s2[i] = 0.0; s_mn[i] = INFINITY; s_mx[i] = -INFINITY; s_cnt[i] = 0u;
+    }
+    __syncthreads();
+
+    const VT *values = reinterpret_cast<const VT *>(a.values);
+    const ZT *zones = reinterpret_cast<const ZT *>(a.zones);
+    const bool v_al = (reinterpret_cast<uintptr_t>(values) & 15) == 0;
+    const bool z_al = (reinterpret_cast<uintptr_t>(zones) & 15) == 0;
+
+    ZhRun run;
+    zh_reset<VT>(run);
+    ZT cur_z = ZT(0);
+    bool have = false, cur_ok = false;
+    long long cur_key = 0;
+
+    // merge (key, cnt, s1, s2, mn, mx) into the CTA table, spilling to the global table when the
+    // CTA sees more distinct zones than its table holds
+    auto merge = [&](long long key, unsigned cnt, double s1, double s2, double mn, double mx) {
+        int s = zh_slot(s_keys, kZhLocalCap, key, 48);
+        if (s >= 0) {
+            if (cnt) {
+                atomicAdd(&s_cnt[s], cnt);
+                atomicAdd(&s_s1[s], s1);
+                atomicAdd(&s_s2[s], s2);
+                zh_atomic_min(&s_mn[s], mn);
+                zh_atomic_max(&s_mx[s], mx);
+            }
+        } else {
+            s = zh_slot(a.keys, a.cap, key, a.cap);
+            if (s < 0) { *a.overflow = 1; }
+            else if (cnt) {
+                atomicAdd(&a.count[s], (unsigned long long)cnt);
+                atomicAdd(&a.s1[s], s1);
+                atomicAdd(&a.s2[s], s2);
+                zh_atomic_min(&a.vmin[s], mn);
+                zh_atomic_max(&a.vmax[s], mx);
+            }
+        }
+    };
+    // Flush the private run.  Called by ALL 32 lanes together (`need` says which lanes really
+    // have something to flush).  Zone boundaries usually hit a whole warp-row at once, with every
+    // lane leaving the same zone: then the 32 runs are first combined with warp shuffles and
+    // lane 0 alone touches the table, instead of 32 lanes serialising on the same five atomics.
+    // A zone is registered even when its run holds no valid value (count 0): zones without valid
+    // cells must still be reported (NaN row, zonal.py:153-162).
+    auto flush_all = [&](bool need) {
+        const unsigned full = 0xffffffffu;
+        need = need && cur_ok;
+        const long long key0 = __shfl_sync(full, cur_key, 0);
+        const bool uniform = __all_sync(full, need && cur_key == key0);
+        double mn = sizeof(VT) == 4 ? (double)run.mnf : run.mnd;
+        double mx = sizeof(VT) == 4 ? (double)run.mxf : run.mxd;
+        if (uniform) {
+            unsigned cnt = __reduce_add_sync(full, run.cnt);
+            double s1 = run.s1, s2 = run.s2;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s1 += __shfl_xor_sync(full, s1, o);
+                s2 += __shfl_xor_sync(full, s2, o);
+                mn = fmin(mn, __shfl_xor_sync(full, mn, o));
+                mx = fmax(mx, __shfl_xor_sync(full, mx, o));
+            }
+            if ((threadIdx.x & 31) == 0) merge(key0, cnt, s1, s2, mn, mx);
+        } else if (need) {
+            merge(cur_key, run.cnt, run.s1, run.s2, mn, mx);
+        }
+        __syncwarp();
+        if (need) zh_reset<VT>(run);
+    };
+
+    // Traversal: the raster is cut into strips of 128 columns x segments of kZhSegRows rows; a
+    // warp owns a (segment, strip) task and walks down its rows, lane l owning columns
+    // 4l .. 4l+3 (one 128-bit load per array per row, 512 contiguous bytes per warp-row).
+    // Zone rasters are spatially coherent, so a lane's run of equal zone ids lasts for many
+    // rows and the private accumulator is flushed rarely.  All 32 lanes execute every
+    // iteration (lanes past the raster's right edge just see nv = 0), so the warp stays
+    // converged and can use warp collectives.
+    const int lane = threadIdx.x & 31;
+    const int64_t H = a.n / a.W;
+    const int64_t n_strips = (a.W + 127) / 128;
+    const int64_t n_segs = (H + kZhSegRows - 1) / kZhSegRows;
+    const int64_t n_tasks = n_strips * n_segs;
+    const int64_t warps_total = (int64_t)gridDim.x * (kZhThreads / 32);
+    const bool row_vec = v_al && z_al && (a.W % 4 == 0);
+    for (int64_t task = (int64_t)blockIdx.x * (kZhThreads / 32) + (threadIdx.x >> 5); task < n_tasks;
+         task += warps_total) {
+        const int64_t seg = task / n_strips, strip = task % n_strips;
+        const int64_t x = strip * 128 + 4 * lane;
+        const int64_t y0 = seg * kZhSegRows, y1 = min(y0 + (int64_t)kZhSegRows, H);
+        const int nv = (int)max((int64_t)0, min((int64_t)4, a.W - x));
+        for (int64_t y = y0; y < y1; y += kZhUnroll) {
+            ZhQuad<VT> v[kZhUnroll];
+            ZhQuad<ZT> z[kZhUnroll];
+#pragma unroll
+            for (int u = 0; u < kZhUnroll; ++u) {
+                const int64_t i0 = (y + u) * a.W + x;
+                const int nvu = (y + u < y1) ? nv : 0;
+                v[u] = zh_load<VT>(values, i0, i0 + nvu, row_vec);
+                z[u] = zh_load<ZT>(zones, i0, i0 + nvu, row_vec);
+            }
+#pragma unroll
+            for (int u = 0; u < kZhUnroll; ++u) {
+                const int nvu = (y + u < y1) ? nv : 0;
+                const bool same = have && (z[u].v[0] == cur_z) && (z[u].v[1] == cur_z) &&
+                                  (z[u].v[2] == cur_z) && (z[u].v[3] == cur_z);
+                const bool fast = (nvu == 4) && same;
+                if (!__all_sync(0xffffffffu, fast || nvu == 0)) {
+                    // some lane meets a zone boundary (or a ragged right edge): cell by cell,
+                    // every lane taking part in every (collective) flush
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const bool live = k < nvu;
+                        const ZT zk = z[u].v[k];
+                        const bool change = live && (!have || !(zk == cur_z));
+                        if (__any_sync(0xffffffffu, change)) flush_all(change && have);
+                        if (change) {
+                            cur_z = zk;
+                            have = (zk == zk);
+                            cur_ok = zh_key<ZT>(zk, cur_key);
+                        }
+                        if (live && cur_ok) zh_add<VT>(run, v[u].v[k], a);
+                    }
+                } else if (fast && cur_ok) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) zh_add<VT>(run, v[u].v[k], a);
+                }
+            }
+        }
+    }
+    flush_all(have);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kZhLocalCap; i += blockDim.x) {
+        const long long key = s_keys[i];
+        if (key != kZhEmpty) {
+            const int s = zh_slot(a.keys, a.cap, key, a.cap);
+            if (s < 0) { *a.overflow = 1; continue; }
+            if (s_cnt[i] == 0u) continue;
+            atomicAdd(&a.count[s], (unsigned long long)s_cnt[i]);
+            atomicAdd(&a.s1[s], s_s1[i]);
+            atomicAdd(&a.s2[s], s_s2[i]);
+            zh_atomic_min(&a.vmin[s], s_mn[i]);
+            zh_atomic_max(&a.vmax[s], s_mx[i]);
+        }
+    }
+}
+
+__global__ void zonal_hash_init_kernel(long long *keys, unsigned long long *count, double *s1, double *s2,
+                                       double *vmin, double *vmax, int cap, int *overflow) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) {
+        keys[i] = kZhEmpty;
+        count[i] = 0ull;
+        s1[i] = 0.0; s2[i] = 0.0; vmin[i] = INFINITY; vmax[i] = -INFINITY;
+    }
+    if (i == 0) *overflow = 0;
+}
+
+template <typename VT, typename ZT> static int launch_zh(const ZhArgs &a, cudaStream_t s) {
+    const int64_t H = a.n / a.W;
+    const int64_t n_tasks = ((a.W + 127) / 128) * ((H + kZhSegRows - 1) / kZhSegRows);
+    int64_t grid = (int64_t)sm_count() * 4;
+    const int64_t need = (n_tasks + kZhThreads / 32 - 1) / (kZhThreads / 32);
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    zonal_hash_kernel<VT, ZT><<<(unsigned)grid, kZhThreads, 0, s>>>(a);
+    XRS_CUDA(cudaGetLastError());
+    return XRS_OK;
+}
+
+}  // namespace xrs
+
+using namespace xrs;
+
+extern "C" {
+
+int xrs_zonal_hash_init(int64_t *keys, int64_t *count, double *s1, double *s2, double *vmin, double *vmax, int cap,
+                        int *overflow, xrs_stream_t s) {
+    XRS_REQUIRE(keys && count && s1 && s2 && vmin && vmax && overflow, "NULL pointer");
+    XRS_REQUIRE(cap >= 1024 && (cap & (cap - 1)) == 0, "cap must be a power of two >= 1024");
+    zonal_hash_init_kernel<<<(cap + 255) / 256, 256, 0, (cudaStream_t)s>>>(
+        (long long *)keys, (unsigned long long *)count, s1, s2, vmin, vmax, cap, overflow);
+    XRS_CUDA(cudaGetLastError());
+    return XRS_OK;
+}
+
+int xrs_zonal_hash_accumulate(const void *values, int values_dtype, const void *zones, int zones_dtype, int64_t n,
+                              int64_t row_len, double pivot, int has_nodata, double nodata, int64_t *keys, int64_t *count,
+                              double *s1, double *s2, double *vmin, double *vmax, int cap, int *overflow,
+                              xrs_stream_t s) {
+    if (n <= 0) return XRS_OK;
+    XRS_REQUIRE(values && zones && keys && count && s1 && s2 && vmin && vmax && overflow, "NULL pointer");
+    XRS_REQUIRE(values_dtype == XRS_F32 || values_dtype == XRS_F64, "values must be float32 or float64");
+    XRS_REQUIRE(zones_dtype >= XRS_F32 && zones_dtype <= XRS_I64, "unknown zones dtype");
+    XRS_REQUIRE(cap >= 1024 && (cap & (cap - 1)) == 0, "cap must be a power of two >= 1024");
+    XRS_REQUIRE(row_len >= 1 && n % row_len == 0, "n must be a multiple of row_len");
+    ZhArgs a;
+    a.values = values; a.zones = zones; a.n = n; a.W = row_len; a.pivot = pivot; a.has_nodata = has_nodata; a.nodata = nodata;
+    a.keys = (long long *)keys; a.count = (unsigned long long *)count; a.s1 = s1; a.s2 = s2; a.vmin = vmin;
+    a.vmax = vmax; a.cap = cap; a.overflow = overflow;
+    cudaStream_t st = (cudaStream_t)s;
+    int rc;
+#define XRS_ZH(VT)                                                               \
+    switch (zones_dtype) {                                                       \
+        case XRS_I32: rc = launch_zh<VT, int>(a, st); break;                     \
+        case XRS_I64: rc = launch_zh<VT, long long>(a, st); break;               \
+        case XRS_F32: rc = launch_zh<VT, float>(a, st); break;                   \
+        default: rc = launch_zh<VT, double>(a, st); break;                       \
+    }
+    if (values_dtype == XRS_F32) { XRS_ZH(float) } else { XRS_ZH(double) }
+#undef XRS_ZH
+    return rc;
+}
+
+}  // extern "C"

@@ -37,24 +37,89 @@ def _prepare(t, allow):
     return t.to(torch.int64).contiguous()
 
 
-def discover_zone_ids(zones_t):
-    """Sorted unique finite zone ids of a device zones raster, as a numpy array in the raster's
-    dtype (zonal.py:290 `np.unique(zones[np.isfinite(zones)])`)."""
+_EMPTY_KEY = -(1 << 63)
+
+
+def _sample_pivot(values_t, comm=None):
+    """One global shift p keeps sum((v-p)^2) well conditioned; a strided sample is enough."""
     import torch
-    if zones_t.numel() == 0:
-        return np.empty((0,), dtype=np.float64)
-    if not zones_t.dtype.is_floating_point:
-        zmin, zmax = torch.aminmax(zones_t)
-        zmin, zmax = int(zmin.item()), int(zmax.item())
-        if zmax - zmin < (1 << 26):
-            # presence table over the compact id range (no sort of the raster)
-            present = torch.zeros(zmax - zmin + 1, dtype=torch.bool, device=zones_t.device)
-            present[(zones_t.reshape(-1) - zmin).long()] = True
-            ids = torch.nonzero(present).reshape(-1) + zmin
-            return ids.cpu().numpy()
-        return torch.unique(zones_t).cpu().numpy()
-    flat = zones_t.reshape(-1)
-    return torch.unique(flat[torch.isfinite(flat)]).cpu().numpy()
+    flat = values_t.reshape(-1)
+    step = max(1, flat.numel() // 65536)
+    sample = flat[::step].to(torch.float64)
+    sample = sample[torch.isfinite(sample)]
+    p0 = float(sample.mean().item()) if sample.numel() else 0.0
+    if comm is not None:
+        import torch.distributed as dist
+        pt = torch.tensor([p0], dtype=torch.float64, device=values_t.device)
+        dist.broadcast(pt, src=dist.get_global_rank(comm, 0), group=comm)
+        p0 = float(pt.item())
+    return p0
+
+
+def hash_partials(zones_t, values_t, nodata_values=None, comm=None, cap=1 << 16):
+    """One streaming pass that discovers the zone ids and accumulates their partials
+    (xrs_zonal_hash_accumulate).  Returns (ids, part, pivot): ids = sorted unique finite zone
+    values present in the raster (numpy, in the zones dtype), part = dict of numpy arrays aligned
+    with ids (count int64; s1, s2, min, max float64), pivot = the scalar shift of s1/s2.
+    With `comm`, the tables of all ranks are merged by id."""
+    import torch
+    dev = values_t.device
+    pivot = _sample_pivot(values_t, comm)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    while True:
+        keys = torch.empty(cap, dtype=torch.int64, device=dev)
+        count = torch.empty(cap, dtype=torch.int64, device=dev)
+        s1 = torch.empty(cap, dtype=torch.float64, device=dev)
+        s2 = torch.empty(cap, dtype=torch.float64, device=dev)
+        vmin = torch.empty(cap, dtype=torch.float64, device=dev)
+        vmax = torch.empty(cap, dtype=torch.float64, device=dev)
+        ovf = torch.empty(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            st = stream_ptr(values_t)
+            _lib.call("xrs_zonal_hash_init", P(keys), P(count), P(s1), P(s2), P(vmin), P(vmax), cap, P(ovf), st)
+            _lib.call("xrs_zonal_hash_accumulate", P(values_t), _dtype_code(values_t), P(zones_t),
+                      _dtype_code(zones_t), values_t.numel(), int(values_t.shape[-1]) if values_t.dim() else 1,
+                      pivot, 0 if nodata_values is None else 1,
+                      0.0 if nodata_values is None else float(nodata_values),
+                      P(keys), P(count), P(s1), P(s2), P(vmin), P(vmax), cap, P(ovf), st)
+        if int(ovf.item()) == 0:
+            break
+        if cap >= (1 << 24):
+            raise NotImplementedError("more than 16M distinct zones are not supported")
+        cap *= 16
+    used = torch.nonzero(keys != _EMPTY_KEY).reshape(-1)
+    k = keys[used].cpu().numpy()
+    part = dict(count=count[used].cpu().numpy(), s1=s1[used].cpu().numpy(), s2=s2[used].cpu().numpy(),
+                min=vmin[used].cpu().numpy(), max=vmax[used].cpu().numpy())
+    if zones_t.dtype.is_floating_point:
+        ids = k.view(np.float64).astype(np.float32 if zones_t.dtype == torch.float32 else np.float64)
+    else:
+        ids = k.astype(np.int32 if zones_t.dtype == torch.int32 else np.int64)
+    if comm is not None:
+        import torch.distributed as dist
+        gathered = [None] * dist.get_world_size(comm)
+        dist.all_gather_object(gathered, (ids, part), group=comm)
+        ids, part = merge_tables(gathered)
+    order = np.argsort(ids, kind="stable")
+    return ids[order], {n: a[order] for n, a in part.items()}, pivot
+
+
+def merge_tables(tables):
+    """Merge [(ids, part), ...] from several stripes by zone id (sum / min / max)."""
+    all_ids = np.concatenate([t[0] for t in tables])
+    ids, inv = np.unique(all_ids, return_inverse=True)
+    out = dict(count=np.zeros(len(ids), np.int64), s1=np.zeros(len(ids)), s2=np.zeros(len(ids)),
+               min=np.full(len(ids), np.inf), max=np.full(len(ids), -np.inf))
+    off = 0
+    for tid, part in tables:
+        sl = inv[off:off + len(tid)]
+        off += len(tid)
+        np.add.at(out["count"], sl, part["count"])
+        np.add.at(out["s1"], sl, part["s1"])
+        np.add.at(out["s2"], sl, part["s2"])
+        np.minimum.at(out["min"], sl, part["min"])
+        np.maximum.at(out["max"], sl, part["max"])
+    return ids, out
 
 
 def zonal_partials(zones_t, values_t, ids, nodata_values=None, pivot=None, comm=None):
@@ -65,19 +130,7 @@ def zonal_partials(zones_t, values_t, ids, nodata_values=None, pivot=None, comm=
     nz = len(ids)
     ids_t = torch.as_tensor(np.asarray(ids, dtype=np.float64), device=dev)
     if pivot is None:
-        # one global shift keeps sum((v-p)^2) well conditioned; a strided sample is enough
-        flat = values_t.reshape(-1)
-        step = max(1, flat.numel() // 65536)
-        sample = flat[::step].to(torch.float64)
-        sample = sample[torch.isfinite(sample)]
-        p0 = float(sample.mean().item()) if sample.numel() else 0.0
-        if comm is not None:
-            import torch.distributed as dist
-            pt = torch.tensor([p0], dtype=torch.float64, device=dev)
-            dist.broadcast(pt, src=dist.get_global_rank(comm, 0) if hasattr(dist, "get_global_rank") else 0,
-                           group=comm)
-            p0 = float(pt.item())
-        pivot = np.full(nz, p0, dtype=np.float64)
+        pivot = np.full(nz, _sample_pivot(values_t, comm), dtype=np.float64)
     piv_t = torch.as_tensor(np.asarray(pivot, dtype=np.float64), device=dev)
     count = torch.empty(nz, dtype=torch.int64, device=dev)
     s1 = torch.empty(nz, dtype=torch.float64, device=dev)
@@ -98,6 +151,7 @@ def zonal_partials(zones_t, values_t, ids, nodata_values=None, pivot=None, comm=
                       _dtype_code(zones_t), values_t.numel(), P(ids_t), nz, P(piv_t),
                       0 if nodata_values is None else 1,
                       0.0 if nodata_values is None else float(nodata_values), use_lut, lut_base,
+                      int(values_t.shape[-1]) if values_t.dim() else 1,
                       P(count), P(s1), P(s2), P(vmin), P(vmax), st)
     if comm is not None and nz:
         import torch.distributed as dist
@@ -153,30 +207,28 @@ def _stats_device(zones, values, zone_ids, stats_funcs, nodata_values, return_ty
     if "majority" in names:
         raise NotImplementedError("'majority' is not available on the B200 backend yet "
                                   "(SURVEY.md section 8f rank 2)")
-    unique_zones = discover_zone_ids(zt)
-    if comm is not None:
-        # union of the ids seen by every stripe
-        import torch.distributed as dist
-        gathered = [None] * dist.get_world_size(comm)
-        dist.all_gather_object(gathered, unique_zones, group=comm)
-        unique_zones = np.unique(np.concatenate([np.asarray(g) for g in gathered]))
+    unique_zones, part_all, pivot0 = hash_partials(zt, vt, nodata_values, comm=comm)
     zdtype = unique_zones.dtype
     if zone_ids is None:
         sel = unique_zones
+        part = part_all
     else:
         sel = np.array([z for z in np.unique(zone_ids) if z in unique_zones], dtype=zdtype)
-    part, pivot = zonal_partials(zt, vt, sel, nodata_values, comm=comm)
-    if vt.dtype == torch.float64 and len(sel) and any(s in names for s in ("std", "var")):
-        # second pass about the per-zone means: numpy's two-pass variance, to ~1e-15
-        cnt = part["count"].astype(np.float64)
-        with np.errstate(invalid="ignore", divide="ignore"):
-            means = np.where(cnt > 0, pivot + part["s1"] / cnt, 0.0)
-        part2, piv2 = zonal_partials(zt, vt, sel, nodata_values, pivot=means, comm=comm)
-        part = dict(part)
-        cols = finalize(part, pivot, [s for s in names if s not in ("std", "var")])
-        cols.update(finalize(part2, piv2, [s for s in names if s in ("std", "var")]))
-    else:
-        cols = finalize(part, pivot, names)
+        pos = np.searchsorted(unique_zones, sel)
+        part = {n: a[pos] for n, a in part_all.items()}
+    pivot = np.full(len(sel), pivot0)
+    cols = finalize(part, pivot, [s for s in names if s not in ("std", "var")])
+    sv = [s for s in names if s in ("std", "var")]
+    if sv:
+        if vt.dtype == torch.float64 and len(sel):
+            # second pass about the per-zone means: numpy's two-pass variance, to ~1e-15
+            cnt = part["count"].astype(np.float64)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                means = np.where(cnt > 0, pivot + part["s1"] / cnt, 0.0)
+            part2, piv2 = zonal_partials(zt, vt, sel, nodata_values, pivot=means, comm=comm)
+            cols.update(finalize(part2, piv2, sv))
+        else:
+            cols.update(finalize(part, pivot, sv))
     if return_type == 'pandas.DataFrame':
         d = {"zone": sel}
         for s in names:
