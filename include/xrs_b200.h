@@ -176,6 +176,14 @@ int xrs_zonal_hash_accumulate(const void *values, int values_dtype, const void *
                               double *s2, double *vmin, double *vmax, int cap, int *overflow,
                               xrs_stream_t s);
 
+/* `majority` (zonal.py:56-68): counts (zone, value) pairs of float32 values / int32 zones into
+ * a hash table (keys/count of `cap` entries, initialised with xrs_zonal_hash_init; key =
+ * (zone << 32) | float32 bits of the value, -0.0 folded into +0.0).  The caller picks the most
+ * frequent value per zone (smallest value on ties). */
+int xrs_zonal_pair_count(const float *values, const int32_t *zones, int64_t n, int64_t row_len,
+                         int has_nodata, double nodata, int64_t *keys, int64_t *count, int cap,
+                         int *overflow, xrs_stream_t s);
+
 /* ------------------------------------------------------------------ host-buffer (end-to-end)
  * Same operators on HOST rasters: the library stripes the raster over rows, and overlaps
  * host->device copies, kernels and device->host copies on internal streams.  `op` selects

@@ -273,3 +273,120 @@ def test_large_zonal_blocks_and_scatter(xb):
         np.testing.assert_array_equal(np.asarray(df["max"]), ref["max"])
         for c in ("mean", "sum", "std", "var"):
             np.testing.assert_allclose(np.asarray(df[c]), ref[c], rtol=1e-5, err_msg=c)
+
+
+def test_row_stripes_are_partition_invariant(xb):
+    """an N-stripe result must equal the single-raster result bit for bit.  The
+    stripes (with 1-row halos cut from the full raster, as the NCCL exchange would deliver
+    them) are processed one after the other on this GPU."""
+    from xrspatial_b200.stripes import split_rows
+    rng = np.random.default_rng(21)
+    z = terrain(rng, 1000, 768, nans=0.002)
+    full = dev(z)
+    ops = {"slope": xb.slope, "aspect": xb.aspect, "curvature": xb.curvature, "hillshade": xb.hillshade,
+           "mean": xb.mean}
+    whole = {k: host(f(da(xb, full))) for k, f in ops.items()}
+    for world in (2, 3, 8):
+        parts = {k: [] for k in ops}
+        for (y0, y1) in split_rows(z.shape[0], world):
+            top = 1 if y0 > 0 else 0
+            bot = 1 if y1 < z.shape[0] else 0
+            stripe = full[y0 - top:y1 + bot].contiguous()
+            for k, f in ops.items():
+                out = f(da(xb, stripe)).data
+                parts[k].append(out[top:top + (y1 - y0)].cpu().numpy())
+        for k in ops:
+            np.testing.assert_array_equal(np.concatenate(parts[k]), whole[k], err_msg="%s world=%d" % (k, world))
+
+
+def _stripe_worker(rank, world, port, H, W, q):
+    import os
+    import sys
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch.distributed as dist
+    import xrspatial_b200 as xbm
+    from xrspatial_b200.stripes import RowStripes
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        rng = np.random.default_rng(33)
+        z = terrain(rng, H, W, nans=0.002)
+        zones = ((np.arange(H)[:, None] // 64) * 8 + np.arange(W)[None, :] // 64).astype(np.int32)
+        st = RowStripes(H, W, radius=1, device=torch.device("cuda", rank))
+        st.interior.copy_(torch.from_numpy(z[st.y0:st.y1]))
+        st.exchange()
+        res = {}
+        for name, fn in (("slope", xbm.slope), ("hillshade", xbm.hillshade), ("mean", xbm.mean)):
+            res[name] = st.apply(fn, attrs={"res": (30.0, 30.0)}).cpu().numpy()
+        zagg = xbm.DataArray(torch.from_numpy(zones[st.y0:st.y1]).cuda(), dims=("y", "x"))
+        vagg = xbm.DataArray(st.interior, dims=("y", "x"))
+        df = xbm.zonal_stats(zagg, vagg, comm=dist.group.WORLD)
+        q.put((rank, st.y0, st.y1, res, {c: np.asarray(df[c]) for c in df.columns}))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_stripes_match_single_gpu(xb):
+    """Real NCCL halo exchange + zonal all-gather merge on 2 GPUs (skipped on 1-GPU boxes)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    H, W = 600, 512
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_stripe_worker, args=(r, 2, port, H, W, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(33)
+    z = terrain(rng, H, W, nans=0.002)
+    zones = ((np.arange(H)[:, None] // 64) * 8 + np.arange(W)[None, :] // 64).astype(np.int32)
+    agg = da(xb, dev(z))
+    for name, fn in (("slope", xb.slope), ("hillshade", xb.hillshade), ("mean", xb.mean)):
+        whole = host(fn(agg))
+        stitched = np.concatenate([g[3][name] for g in got])
+        np.testing.assert_array_equal(stitched, whole, err_msg=name)
+    df = xb.zonal_stats(da(xb, dev(zones)), agg)
+    for c in df.columns:
+        a, b = np.asarray(df[c]), got[0][4][c]
+        if c in ("zone", "count", "min", "max"):
+            np.testing.assert_array_equal(a, b, err_msg=c)
+        else:
+            np.testing.assert_allclose(a, b, rtol=1e-9, equal_nan=True, err_msg=c)
+
+
+def test_zonal_majority(xb, known, refout):
+    # ties -> smallest value (test_zonal.py:567-590)
+    zones = np.array([[1, 1, 1, 1], [1, 1, 2, 2], [2, 2, 2, 2]], dtype=np.int32)
+    values = np.array([[1, 1, 2, 2], [3, 3, 5, 5], [5, 5, 6, 6]], dtype=np.float32)
+    df = xb.zonal_stats(da(xb, dev(zones)), da(xb, dev(values)), stats_funcs=["majority"])
+    np.testing.assert_array_equal(np.asarray(df["zone"]), [1, 2])
+    np.testing.assert_array_equal(np.asarray(df["majority"]), [1, 5])
+    # test_zonal.py:61-75 default table incl. majority (float zones with a NaN, inf / NaN values)
+    df = xb.zonal_stats(da(xb, dev(known["zonal.data_zones"])), da(xb, dev(known["zonal.data_values_2d"])),
+                        stats_funcs=["mean", "max", "min", "sum", "std", "var", "count", "majority"])
+    for c in ("zone", "mean", "max", "min", "sum", "std", "var", "count", "majority"):
+        np.testing.assert_allclose(np.asarray(df[c], dtype=np.float64), known["zonal.result_default_stats." + c],
+                                   rtol=1e-5, atol=1e-7, err_msg=c)
+    # continuous values: every value unique -> majority is the zone minimum (reference output)
+    df = xb.zonal_stats(da(xb, dev(refout["zonal.zones_i32"])), da(xb, dev(refout["zonal.values_f32"])),
+                        stats_funcs=["majority", "count"])
+    np.testing.assert_array_equal(np.asarray(df["majority"]), refout["zonal.f32_i32.majority"])
+    # categorical raster vs the oracle
+    rng = np.random.default_rng(9)
+    zc = rng.integers(0, 37, size=(300, 256)).astype(np.int32)
+    vc = rng.integers(0, 9, size=(300, 256)).astype(np.float32)
+    vc[rng.random(vc.shape) < 0.01] = np.nan
+    df = xb.zonal_stats(da(xb, dev(zc)), da(xb, dev(vc)), stats_funcs=["majority"])
+    ref = o.zonal_stats(zc, vc, stats_funcs=["majority"])
+    np.testing.assert_array_equal(np.asarray(df["majority"]), ref["majority"])

@@ -87,11 +87,16 @@ conv2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
 
+        // Input row j of the thread's window feeds output row r with kernel row ky = j - r.
+        // Rows 3 .. kh-1 feed all four output rows and chunks [off .. off+kw) that lie fully
+        // inside the kernel need no tap test: that common case is straight-line DFMA code;
+        // the (few) edge rows / edge chunks take the generic, predicated path.
         const int rows_in = 4 + g.kh - 1;
+        const int n_taps = g.off + g.kw;
         for (int j = 0; j < rows_in; ++j) {
             const double *rowp = tile64 + (size_t)(ty * 4 + j) * g.sw + 4 * tx;
-            // taps are indexed from the aligned tile origin: tap kx sits at column kx + off
-            for (int kb = 0; kb < g.off + g.kw; kb += 4) {
+            const bool full_rows = (j >= 3) && (j < g.kh);
+            for (int kb = 0; kb < n_taps; kb += 4) {
                 double v[8];
                 const double2 q0 = *reinterpret_cast<const double2 *>(rowp + kb);
                 const double2 q1 = *reinterpret_cast<const double2 *>(rowp + kb + 2);
@@ -99,17 +104,32 @@ conv2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
                 const double2 q3 = *reinterpret_cast<const double2 *>(rowp + kb + 6);
                 v[0] = q0.x; v[1] = q0.y; v[2] = q1.x; v[3] = q1.y;
                 v[4] = q2.x; v[5] = q2.y; v[6] = q3.x; v[7] = q3.y;
+                const bool full_chunk = (kb >= g.off) && (kb + 4 <= n_taps);
+                if (full_rows && full_chunk) {
+                    const double *w0 = cw.w + (j * g.kw + kb - g.off);  // kernel row j, taps kb-off ..
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int ky = j - r;
-                    if (ky >= 0 && ky < g.kh) {
+                    for (int r = 0; r < 4; ++r) {
+                        const double *wr = w0 - r * g.kw;            // kernel row j - r
 #pragma unroll
                         for (int tt = 0; tt < 4; ++tt) {
-                            const int kx = kb + tt - g.off;
-                            if (kx >= 0 && kx < g.kw) {
-                                const double wv = cw.w[ky * g.kw + kx];
+                            const double wv = wr[tt];
 #pragma unroll
-                                for (int c = 0; c < 4; ++c) acc[r][c] = fma(wv, v[c + tt], acc[r][c]);
+                            for (int c = 0; c < 4; ++c) acc[r][c] = fma(wv, v[c + tt], acc[r][c]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int ky = j - r;
+                        if (ky >= 0 && ky < g.kh) {
+#pragma unroll
+                            for (int tt = 0; tt < 4; ++tt) {
+                                const int kx = kb + tt - g.off;
+                                if (kx >= 0 && kx < g.kw) {
+                                    const double wv = cw.w[ky * g.kw + kx];
+#pragma unroll
+                                    for (int c = 0; c < 4; ++c) acc[r][c] = fma(wv, v[c + tt], acc[r][c]);
+                                }
                             }
                         }
                     }

@@ -310,9 +310,11 @@ int launch_stencil3(const typename Op::in_t *in, int64_t in_pitch_bytes, const t
                                 (size_t)kWarpsPerCta * STAGES * sizeof(uint64_t);
         auto kern = stencil3_tma_kernel<Op, ROWS, STAGES>;
         XRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = (int)((227 * 1024) / (smem + 1024));
+        // persistent grid: as many CTAs as fit on an SM (registers / shared memory), times the SMs
+        int per_sm = 0;
+        XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerCta * 32, smem));
         if (per_sm < 1) per_sm = 1;
-        if (per_sm > 2) per_sm = 2;  // register budget: <= 128 regs x 512 threads
+        if (per_sm > 4) per_sm = 4;
         int64_t grid = (int64_t)sms * per_sm;
         if (grid > ctas_needed) grid = ctas_needed;
         li.used_tma = 1;

@@ -302,6 +302,89 @@ __global__ void __launch_bounds__(kZhThreads) zonal_hash_kernel(const __grid_con
     }
 }
 
+// ----------------------------------------------------------------------------- majority
+// `majority` (zonal.py:56-68: np.unique(values, return_counts) -> the most frequent value, the
+// smallest one on ties) needs per-zone value histograms.  One pass counts (zone, value) PAIRS in
+// the same kind of hash table: key = (int32 zone id << 32) | float32 bit pattern of the value.
+// The host then picks, per zone, the value with the largest count.  Meant for categorical
+// value rasters (few distinct values per zone); `cap` bounds the number of distinct pairs.
+struct ZpArgs {
+    const float *values;
+    const int *zones;
+    int64_t n, W;
+    int has_nodata;
+    float nodata;
+    long long *keys;
+    unsigned long long *count;
+    int cap;
+    int *overflow;
+};
+
+__global__ void __launch_bounds__(kZhThreads) zonal_pair_kernel(const __grid_constant__ ZpArgs a) {
+    __shared__ long long s_keys[kZhLocalCap * 2];
+    __shared__ unsigned s_cnt[kZhLocalCap * 2];
+    constexpr int kCap = kZhLocalCap * 2;
+    for (int i = threadIdx.x; i < kCap; i += blockDim.x) { s_keys[i] = kZhEmpty; s_cnt[i] = 0u; }
+    __syncthreads();
+    const bool al = ((reinterpret_cast<uintptr_t>(a.values) | reinterpret_cast<uintptr_t>(a.zones)) & 15) == 0 &&
+                    (a.W % 4 == 0);
+    long long cur_key = kZhEmpty;
+    unsigned run = 0u;
+    auto merge = [&](long long key, unsigned cnt) {
+        int s = zh_slot(s_keys, kCap, key, 64);
+        if (s >= 0) { atomicAdd(&s_cnt[s], cnt); return; }
+        s = zh_slot(a.keys, a.cap, key, a.cap);
+        if (s < 0) *a.overflow = 1; else atomicAdd(&a.count[s], (unsigned long long)cnt);
+    };
+    auto flush_all = [&](bool need) {
+        const unsigned full = 0xffffffffu;
+        need = need && run != 0u;
+        const long long key0 = __shfl_sync(full, cur_key, 0);
+        if (__all_sync(full, need && cur_key == key0)) {
+            const unsigned cnt = __reduce_add_sync(full, run);
+            if ((threadIdx.x & 31) == 0) merge(key0, cnt);
+        } else if (need) {
+            merge(cur_key, run);
+        }
+        __syncwarp();
+        if (need) run = 0u;
+    };
+    const int lane = threadIdx.x & 31;
+    const int64_t H = a.n / a.W;
+    const int64_t n_strips = (a.W + 127) / 128, n_segs = (H + kZhSegRows - 1) / kZhSegRows;
+    const int64_t warps_total = (int64_t)gridDim.x * (kZhThreads / 32);
+    for (int64_t task = (int64_t)blockIdx.x * (kZhThreads / 32) + (threadIdx.x >> 5); task < n_strips * n_segs;
+         task += warps_total) {
+        const int64_t seg = task / n_strips, strip = task % n_strips;
+        const int64_t x = strip * 128 + 4 * lane;
+        const int64_t y0 = seg * kZhSegRows, y1 = min(y0 + (int64_t)kZhSegRows, H);
+        const int nv = (int)max((int64_t)0, min((int64_t)4, a.W - x));
+        for (int64_t y = y0; y < y1; ++y) {
+            const int64_t i0 = y * a.W + x;
+            const ZhQuad<float> v = zh_load<float>(a.values, i0, i0 + nv, al);
+            const ZhQuad<int> z = zh_load<int>(a.zones, i0, i0 + nv, al);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float f = v.v[k] + 0.0f;  // -0.0 -> +0.0
+                const bool ok = k < nv && (fabsf(f) <= 3.402823466e38f) && !(a.has_nodata && f == a.nodata);
+                const long long key = ((long long)z.v[k] << 32) | (long long)__float_as_uint(f);
+                const bool change = ok && key != cur_key;
+                if (__any_sync(0xffffffffu, change)) flush_all(change);
+                if (change) cur_key = key;
+                if (ok) run += 1u;
+            }
+        }
+    }
+    flush_all(true);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kCap; i += blockDim.x) {
+        if (s_keys[i] != kZhEmpty && s_cnt[i]) {
+            const int s = zh_slot(a.keys, a.cap, s_keys[i], a.cap);
+            if (s < 0) *a.overflow = 1; else atomicAdd(&a.count[s], (unsigned long long)s_cnt[i]);
+        }
+    }
+}
+
 __global__ void zonal_hash_init_kernel(long long *keys, unsigned long long *count, double *s1, double *s2,
                                        double *vmin, double *vmax, int cap, int *overflow) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -367,6 +450,26 @@ int xrs_zonal_hash_accumulate(const void *values, int values_dtype, const void *
     if (values_dtype == XRS_F32) { XRS_ZH(float) } else { XRS_ZH(double) }
 #undef XRS_ZH
     return rc;
+}
+
+int xrs_zonal_pair_count(const float *values, const int32_t *zones, int64_t n, int64_t row_len, int has_nodata,
+                         double nodata, int64_t *keys, int64_t *count, int cap, int *overflow, xrs_stream_t s) {
+    if (n <= 0) return XRS_OK;
+    XRS_REQUIRE(values && zones && keys && count && overflow, "NULL pointer");
+    XRS_REQUIRE(cap >= 1024 && (cap & (cap - 1)) == 0, "cap must be a power of two >= 1024");
+    XRS_REQUIRE(row_len >= 1 && n % row_len == 0, "n must be a multiple of row_len");
+    ZpArgs a;
+    a.values = values; a.zones = (const int *)zones; a.n = n; a.W = row_len; a.has_nodata = has_nodata;
+    a.nodata = (float)nodata; a.keys = (long long *)keys; a.count = (unsigned long long *)count; a.cap = cap;
+    a.overflow = overflow;
+    const int64_t n_tasks = ((row_len + 127) / 128) * ((n / row_len + kZhSegRows - 1) / kZhSegRows);
+    int64_t grid = (int64_t)sm_count() * 4;
+    const int64_t need = (n_tasks + kZhThreads / 32 - 1) / (kZhThreads / 32);
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    zonal_pair_kernel<<<(unsigned)grid, kZhThreads, 0, (cudaStream_t)s>>>(a);
+    XRS_CUDA(cudaGetLastError());
+    return XRS_OK;
 }
 
 }  // extern "C"

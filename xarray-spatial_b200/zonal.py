@@ -104,6 +104,65 @@ def hash_partials(zones_t, values_t, nodata_values=None, comm=None, cap=1 << 16)
     return ids[order], {n: a[order] for n, a in part.items()}, pivot
 
 
+def majority_by_zone(zones_t, values_t, nodata_values=None, comm=None, cap=1 << 20):
+    """dict zone id -> majority value (most frequent valid value, smallest on ties): one pass of
+    xrs_zonal_pair_count over (int32 zone, float32 value) pairs, then a tiny host group-by."""
+    import torch
+    dev = values_t.device
+    if zones_t.dtype != torch.int32:
+        if zones_t.dtype.is_floating_point:
+            zi = zones_t.to(torch.int32)
+            if not bool((zi.to(zones_t.dtype) == zones_t)[torch.isfinite(zones_t)].all()):
+                raise NotImplementedError("'majority' needs integer-valued zone ids")
+        else:
+            zi = zones_t.to(torch.int32)
+            if not bool((zi.to(zones_t.dtype) == zones_t).all()):
+                raise NotImplementedError("'majority' needs zone ids that fit in int32")
+        finite_zone = torch.isfinite(zones_t) if zones_t.dtype.is_floating_point else None
+    else:
+        zi, finite_zone = zones_t, None
+    vf = values_t.to(torch.float32)
+    if values_t.dtype != torch.float32 and not bool(((vf.to(values_t.dtype) == values_t) | ~torch.isfinite(values_t)).all()):
+        raise NotImplementedError("'majority' needs values that are exact in float32")
+    if finite_zone is not None:
+        vf = torch.where(finite_zone, vf, torch.full_like(vf, float("nan")))  # cells of NaN zones drop out
+    P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    while True:
+        keys = torch.empty(cap, dtype=torch.int64, device=dev)
+        count = torch.empty(cap, dtype=torch.int64, device=dev)
+        dummy = torch.empty((4, cap), dtype=torch.float64, device=dev)
+        ovf = torch.empty(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            st = stream_ptr(vf)
+            _lib.call("xrs_zonal_hash_init", P(keys), P(count), P(dummy[0]), P(dummy[1]), P(dummy[2]), P(dummy[3]),
+                      cap, P(ovf), st)
+            _lib.call("xrs_zonal_pair_count", P(vf.contiguous()), P(zi.contiguous()), vf.numel(),
+                      int(vf.shape[-1]) if vf.dim() else 1, 0 if nodata_values is None else 1,
+                      0.0 if nodata_values is None else float(nodata_values), P(keys), P(count), cap, P(ovf), st)
+        if int(ovf.item()) == 0:
+            break
+        if cap >= (1 << 26):
+            raise NotImplementedError("too many distinct (zone, value) pairs for 'majority'")
+        cap *= 8
+    used = torch.nonzero(keys != _EMPTY_KEY).reshape(-1)
+    k = keys[used].cpu().numpy()
+    c = count[used].cpu().numpy()
+    if comm is not None:
+        import torch.distributed as dist
+        gathered = [None] * dist.get_world_size(comm)
+        dist.all_gather_object(gathered, (k, c), group=comm)
+        k = np.concatenate([g[0] for g in gathered])
+        c = np.concatenate([g[1] for g in gathered])
+        k, inv = np.unique(k, return_inverse=True)
+        c = np.bincount(inv, weights=c).astype(np.int64)
+    zone = (k >> 32).astype(np.int64)
+    val = (k & 0xFFFFFFFF).astype(np.uint32).view(np.float32).astype(np.float64)
+    order = np.lexsort((val, -c, zone))      # per zone: highest count first, then smallest value
+    zone, val = zone[order], val[order]
+    first = np.r_[True, zone[1:] != zone[:-1]]
+    return dict(zip(zone[first].tolist(), val[first].tolist()))
+
+
 def merge_tables(tables):
     """Merge [(ids, part), ...] from several stripes by zone id (sum / min / max)."""
     all_ids = np.concatenate([t[0] for t in tables])
@@ -204,9 +263,6 @@ def _stats_device(zones, values, zone_ids, stats_funcs, nodata_values, return_ty
     if len(vt.shape) > 2:
         raise TypeError('3D inputs not supported for the device backend')
     names = list(stats_funcs)
-    if "majority" in names:
-        raise NotImplementedError("'majority' is not available on the B200 backend yet "
-                                  "(SURVEY.md section 8f rank 2)")
     unique_zones, part_all, pivot0 = hash_partials(zt, vt, nodata_values, comm=comm)
     zdtype = unique_zones.dtype
     if zone_ids is None:
@@ -217,7 +273,11 @@ def _stats_device(zones, values, zone_ids, stats_funcs, nodata_values, return_ty
         pos = np.searchsorted(unique_zones, sel)
         part = {n: a[pos] for n, a in part_all.items()}
     pivot = np.full(len(sel), pivot0)
-    cols = finalize(part, pivot, [s for s in names if s not in ("std", "var")])
+    cols = finalize(part, pivot, [s for s in names if s not in ("std", "var", "majority")])
+    if "majority" in names:
+        maj = majority_by_zone(zt, vt, nodata_values, comm=comm)
+        cols["majority"] = np.array([maj.get(int(z), np.nan) if float(z).is_integer() else np.nan for z in sel],
+                                    dtype=np.float64)
     sv = [s for s in names if s in ("std", "var")]
     if sv:
         if vt.dtype == torch.float64 and len(sel):
@@ -267,8 +327,8 @@ def stats(zones, values, zone_ids=None,
     """Per-zone summary statistics (zonal.py:422-667).
 
     Differences from the reference, all explicit: `stats_funcs` must name built-in statistics
-    (custom callables cannot run on the device), `majority` is not available yet, and the
-    default list therefore omits it.  `comm` (optional torch.distributed group) marks `zones`
+    (custom callables cannot run on the device); `majority` costs a second pass (a (zone, value)
+    pair histogram) and is therefore not in the default list -- name it to get it.  `comm` (optional torch.distributed group) marks `zones`
     and `values` as this rank's row stripe of a larger raster.
     """
     if isinstance(values, Dataset):
