@@ -219,9 +219,51 @@ __device__ __forceinline__ float focal_reduce(const Fetch &fetch, const MaskBits
     }
 }
 
+// Register-blocked like conv2d_kernel: a thread owns 4 x 4 outputs, walks the input rows of its
+// window once (twice for var / std), loads 8 cells per 4-tap chunk with two LDS.128 and feeds
+// every (output row, tap) pair whose mask bit is set.  Taps are visited in row-major window
+// order for each output, so the float32 `sum` is bit-identical to np.nansum on the scratch.
+template <typename F>
+__device__ __forceinline__ void focal_sweep(const float *tile32, const MaskBits &mask, const TileGeom &g, int tx,
+                                            int ty, F &&f) {
+    const int rows_in = 4 + g.kh - 1;
+    const int n_taps = g.off + g.kw;
+    for (int j = 0; j < rows_in; ++j) {
+        const float *rowp = tile32 + (size_t)(ty * 4 + j) * g.sw + 4 * tx;
+        for (int kb = 0; kb < n_taps; kb += 4) {
+            const float4 q0 = *reinterpret_cast<const float4 *>(rowp + kb);
+            const float4 q1 = *reinterpret_cast<const float4 *>(rowp + kb + 4);
+            const float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            // NaN test and f64 widening once per loaded cell, not once per (output, tap) use
+            bool ok[8];
+            double dv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                ok[i] = (v[i] == v[i]);
+                dv[i] = (double)v[i];
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int ky = j - r;
+                if (ky >= 0 && ky < g.kh) {
+#pragma unroll
+                    for (int tt = 0; tt < 4; ++tt) {
+                        const int kx = kb + tt - g.off;
+                        if (kx >= 0 && kx < g.kw && mask.m[ky * g.kw + kx]) {  // warp-uniform
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) f(r, c, v[c + tt], dv[c + tt], ok[c + tt]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int STAT>
 __global__ void __launch_bounds__(256)
 focal_stat_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MaskBits mask,
-                  float *__restrict__ out, int64_t out_pitch_elems, const TileGeom g, int stat) {
+                  float *__restrict__ out, int64_t out_pitch_elems, const TileGeom g) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int nbox = (g.sh + g.box_h - 1) / g.box_h;
     const size_t tile_cells = (size_t)nbox * g.box_h * g.sw;
@@ -233,6 +275,7 @@ focal_stat_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         mbar_fence_init();
     }
     __syncthreads();
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t n_tiles = (int64_t)g.tiles_x * g.tiles_y;
     uint32_t parity = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -240,15 +283,72 @@ focal_stat_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         const int x0 = tile_x * kTileW, y0 = tile_y * kTileH;
         load_tile_tma(&tmap, tile32, bar, g, x0, y0, parity);
         parity ^= 1u;
-        for (int o = threadIdx.x; o < kTileW * kTileH; o += blockDim.x) {
-            const int lx = o % kTileW, ly = o / kTileW;
-            const int64_t xo = (int64_t)x0 + lx, yo = (int64_t)y0 + ly;
-            if (xo < g.W && yo < g.H) {
-                const float *base = tile32 + (size_t)ly * g.sw + lx + g.off;
-                const int sw = g.sw;
-                auto fetch = [base, sw](int ky, int kx) { return base[ky * sw + kx]; };
-                out[yo * out_pitch_elems + xo] = focal_reduce(fetch, mask, g.kh, g.kw, stat);
+        float res[4][4];
+        if constexpr (STAT == XRS_STAT_MEAN || STAT == XRS_STAT_VAR || STAT == XRS_STAT_STD) {
+            double sum[4][4];
+            int cnt[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) sum[r][c] = 0.0, cnt[r][c] = 0;
+            focal_sweep(tile32, mask, g, tx, ty, [&](int r, int c, float, double d, bool ok) {
+                sum[r][c] += ok ? d : 0.0;
+                cnt[r][c] += ok ? 1 : 0;
+            });
+            if constexpr (STAT == XRS_STAT_MEAN) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) res[r][c] = (float)(sum[r][c] / (double)cnt[r][c]);
+            } else {
+                double ssd[4][4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) sum[r][c] = sum[r][c] / (double)cnt[r][c], ssd[r][c] = 0.0;
+                focal_sweep(tile32, mask, g, tx, ty, [&](int r, int c, float, double dvv, bool ok) {
+                    const double d = dvv - sum[r][c];
+                    ssd[r][c] += ok ? d * d : 0.0;
+                });
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const double var = ssd[r][c] / (double)cnt[r][c];
+                        res[r][c] = (float)(STAT == XRS_STAT_VAR ? var : sqrt(var));
+                    }
             }
+        } else if constexpr (STAT == XRS_STAT_SUM) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) res[r][c] = 0.f;
+            focal_sweep(tile32, mask, g, tx, ty, [&](int r, int c, float v, double, bool ok) { res[r][c] += ok ? v : 0.f; });
+        } else {
+            float mn[4][4], mx[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) mn[r][c] = mx[r][c] = nan_of<float>();
+            focal_sweep(tile32, mask, g, tx, ty, [&](int r, int c, float v, double, bool ok) {
+                if (ok) {
+                    if (!(mn[r][c] < v)) mn[r][c] = v;
+                    if (!(mx[r][c] > v)) mx[r][c] = v;
+                }
+            });
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    res[r][c] = STAT == XRS_STAT_MIN ? mn[r][c] : STAT == XRS_STAT_MAX ? mx[r][c] : mx[r][c] - mn[r][c];
+        }
+        const int64_t xo = (int64_t)x0 + 4 * tx;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int64_t yo = (int64_t)y0 + ty * 4 + r;
+            if (yo < g.H && xo < g.W)  // W % 4 == 0 on this path
+                __stcs(reinterpret_cast<float4 *>(out + yo * out_pitch_elems + xo),
+                       make_float4(res[r][0], res[r][1], res[r][2], res[r][3]));
         }
         __syncthreads();
     }
@@ -358,14 +458,23 @@ int xrs_focal_stat_f32(const float *in, int64_t in_pitch, float *out, int64_t ou
         const int nbox = (g.sh + g.box_h - 1) / g.box_h;
         const size_t smem = (size_t)nbox * g.box_h * g.sw * 4 + 16;
         if (smem <= 227 * 1024) {
-            XRS_CUDA(cudaFuncSetAttribute(focal_stat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int per_sm = (int)((227 * 1024) / (smem + 1024));
-            if (per_sm > 4) per_sm = 4;
+            if (per_sm > 3) per_sm = 3;
             if (per_sm < 1) per_sm = 1;
             int64_t grid = (int64_t)sms * per_sm;
             const int64_t n_tiles = (int64_t)g.tiles_x * g.tiles_y;
             if (grid > n_tiles) grid = n_tiles;
-            focal_stat_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)s>>>(tmap, mask, out, out_pitch / 4, g, stat);
+#define XRS_FS(ST)                                                                                              \
+    case ST:                                                                                                    \
+        XRS_CUDA(cudaFuncSetAttribute(focal_stat_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                      (int)smem));                                                              \
+        focal_stat_kernel<ST><<<(unsigned)grid, 256, smem, (cudaStream_t)s>>>(tmap, mask, out, out_pitch / 4, g); \
+        break;
+            switch (stat) {
+                XRS_FS(XRS_STAT_MEAN) XRS_FS(XRS_STAT_SUM) XRS_FS(XRS_STAT_MIN) XRS_FS(XRS_STAT_MAX)
+                XRS_FS(XRS_STAT_STD) XRS_FS(XRS_STAT_RANGE) XRS_FS(XRS_STAT_VAR)
+            }
+#undef XRS_FS
             XRS_CUDA(cudaGetLastError());
             return XRS_OK;
         }

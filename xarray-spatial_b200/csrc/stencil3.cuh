@@ -314,7 +314,7 @@ int launch_stencil3(const typename Op::in_t *in, int64_t in_pitch_bytes, const t
         int per_sm = 0;
         XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerCta * 32, smem));
         if (per_sm < 1) per_sm = 1;
-        if (per_sm > 4) per_sm = 4;
+        if (per_sm > 2) per_sm = 2;  // measured: 3 CTAs / SM is ~4% slower for hillshade than 2
         int64_t grid = (int64_t)sms * per_sm;
         if (grid > ctas_needed) grid = ctas_needed;
         li.used_tma = 1;
