@@ -108,6 +108,15 @@ int xrs_focal_stat_f32(const float *in, int64_t in_pitch, float *out, int64_t ou
                        int64_t H, int64_t W, const double *kernel, int kh, int kw, int stat,
                        xrs_stream_t s);
 
+/* focal.hotspots (focal.py:1050-1125) = convolve_2d with kernel / kernel.sum(), then
+ * z = (mean - global_mean) / global_std classified into {0, +-90, +-95, +-99} (int8).
+ * xrs_global_stats_f32: partial3[0..2] (device) <- count, sum(v - pivot), sum((v - pivot)^2) over
+ * the non-NaN cells, from which np.nanmean / np.nanstd follow.  (focal.py:881-937) */
+int xrs_global_stats_f32(const float *values, int64_t n, double pivot, double *partial3,
+                         xrs_stream_t s);
+int xrs_hotspots_classify_f32(const float *mean, int64_t n, double global_mean, double global_std,
+                              int8_t *out, xrs_stream_t s);
+
 /* ------------------------------------------------------------------ multispectral
  * Elementwise over n contiguous float32 cells; out is NaN where the denominator is 0. */
 /* multispectral._run_normalized_ratio_cupy (:862) -- ndvi, nbr, nbr2, ndmi */

@@ -249,6 +249,30 @@ def reference_outputs():
     arr = zonal._stats_numpy(zz, zv, [3, 7], {s: zonal._DEFAULT_STATS[s] for s in ("mean", "count")},
                              None, return_type="xarray.DataArray")
     g["zonal.f32_i32.broadcast_mean_count_3_7"] = arr
+
+    # focal.hotspots (focal.py:918-937) on a raster with two bumps, and zonal.crosstab (2-D)
+    import types
+    hz = terrain(rng, 64, 80)
+    hz[20:26, 30:36] += 3000.0
+    hz[45:50, 10:16] -= 2500.0
+    hk = np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]], dtype=float)
+    g["hotspots.dem"] = hz
+    g["hotspots.kernel"] = hk
+    g["hotspots.out"] = focal._hotspots_numpy(types.SimpleNamespace(data=hz), hk)
+    hk5 = np.ones((5, 5))
+    g["hotspots.out_5x5"] = focal._hotspots_numpy(types.SimpleNamespace(data=hz), hk5)
+    cz = rng.integers(0, 6, size=(40, 52)).astype(np.int32)
+    cv = rng.integers(10, 15, size=(40, 52)).astype(np.float32)
+    cv[rng.random(cv.shape) < 0.05] = np.nan
+    cv[cz == 4] = np.nan                      # a zone without any valid value
+    g["crosstab.zones"], g["crosstab.values"] = cz, cv
+    ucats = np.unique(cv[np.isfinite(cv)])
+    for agg in ("count", "percentage"):
+        df = zonal._crosstab_numpy(cz, cv, None, ucats, ucats, None, agg)
+        g["crosstab.%s.columns" % agg] = np.asarray([float(c) for c in df.columns[1:]])
+        g["crosstab.%s.table" % agg] = np.asarray(df.values, dtype=np.float64)
+    df = zonal._crosstab_numpy(cz, cv, [1, 3, 9], ucats, [11.0, 13.0], 12.0, "count")
+    g["crosstab.sub.table"] = np.asarray(df.values, dtype=np.float64)
     return g
 
 

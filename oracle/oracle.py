@@ -222,3 +222,52 @@ def zonal_stats(zones, values, zone_ids=None,
             start = end
         res[name] = col[keep]
     return res
+
+
+# --------------------------------------------------------------------------- hotspots / crosstab
+def hotspots(data, kernel, nthreads=1):
+    """focal.py:918-937 `_hotspots_numpy` + :881-915 `_calc_hotspots_numpy` (int8)."""
+    d = np.asarray(data).astype(np.float32)
+    k = np.asarray(kernel, dtype=np.float64)
+    mean_array = convolve_2d(d, k / k.sum(), nthreads=nthreads)
+    global_mean = np.nanmean(d)
+    global_std = np.nanstd(d)
+    if global_std == 0:
+        raise ZeroDivisionError("Standard deviation of the input raster values is 0.")
+    z = (mean_array - global_mean) / global_std
+    az = np.abs(z)
+    with np.errstate(invalid="ignore"):
+        p = np.where(az >= 2.33, 0.0099, np.where(az >= 1.65, 0.0495, np.where(az >= 1.29, 0.0985, 1.0)))
+        conf = np.where((az > 2.58) & (p < 0.01), 99, np.where((az > 1.96) & (p < 0.05), 95,
+                                                             np.where((az > 1.65) & (p < 0.1), 90, 0)))
+        hc = np.where(z > 0, 1, np.where(z < 0, -1, 0))
+    return (hc * conf).astype(np.int8)
+
+
+def crosstab(zones, values, zone_ids=None, cat_ids=None, agg="count", nodata_values=None):
+    """zonal.py:748-810 `_crosstab_numpy` for 2-D values: dict(zone=..., <cat>=counts|percentages)."""
+    zones = np.asarray(zones)
+    values = np.asarray(values)
+    valid = np.isfinite(values)
+    if nodata_values is not None:
+        valid &= values != nodata_values
+    unique_cats = np.unique(values[valid])
+    cats = unique_cats if cat_ids is None else [c for c in cat_ids if c in unique_cats]
+    unique_zones = np.unique(zones[np.isfinite(zones)])
+    sel = unique_zones if zone_ids is None else [z for z in zone_ids if z in unique_zones]
+    res = {"zone": np.asarray(sel)}
+    total = np.array([np.count_nonzero(valid & (zones == z)) for z in sel], dtype=np.float32)
+    # zonal.py:719-727: `cat_start` only advances at SELECTED categories, so a selected category
+    # also collects the cells of the unselected categories just below it (reference behaviour,
+    # kept as is).  With cat_ids=None every category is selected and this is the plain count.
+    prev = -np.inf
+    for c in sorted(cats):
+        cnt = np.array([np.count_nonzero(valid & (zones == z) & (values > prev) & (values <= c)) for z in sel])
+        prev = c
+        if agg == "percentage":
+            t = total.copy()
+            t[t == 0] = np.nan
+            res[c] = cnt / t * 100
+        else:
+            res[c] = cnt
+    return res

@@ -390,3 +390,90 @@ def test_zonal_majority(xb, known, refout):
     df = xb.zonal_stats(da(xb, dev(zc)), da(xb, dev(vc)), stats_funcs=["majority"])
     ref = o.zonal_stats(zc, vc, stats_funcs=["majority"])
     np.testing.assert_array_equal(np.asarray(df["majority"]), ref["majority"])
+
+
+# ----------------------------------------------------------------- BASELINE.json full sizes
+def _interior(t):
+    return t[1:-1, 1:-1]
+
+
+@pytest.mark.parametrize("side", [32768, 65536])
+def test_full_size_properties(xb, side):
+    """Size-independent properties at the benchmark sizes (32768^2 = configs[1], 65536^2 = the
+    striped raster of configs[4]); the oracle cannot run here in seconds, closed forms can."""
+    import math
+    free, _ = torch.cuda.mem_get_info()
+    if free < side * side * 4 * 6:
+        pytest.skip("not enough device memory for a %d^2 raster" % side)
+    H = W = side
+    ys = torch.arange(H, device="cuda", dtype=torch.float32)[:, None]
+    xs = torch.arange(W, device="cuda", dtype=torch.float32)[None, :]
+    ramp = (0.5 * xs + 0.25 * ys).contiguous()          # exact in float32
+    agg = da(xb, ramp, res=(30.0, 30.0))
+    # planar ramp: Horn slope is the same constant in every interior cell, aspect likewise
+    s = xb.slope(agg).data
+    expect = math.degrees(math.atan(math.hypot(0.5 / 30.0, 0.25 / 30.0))) * (57.29578 / (180 / math.pi))
+    si = _interior(s)
+    assert float(si.min()) == float(si.max())
+    assert abs(float(si[0, 0]) - expect) <= 1e-5 * expect
+    assert bool(torch.isnan(s[0]).all() and torch.isnan(s[-1]).all() and torch.isnan(s[:, 0]).all()
+                and torch.isnan(s[:, -1]).all())
+    del s, si
+    a = xb.aspect(agg).data
+    ai = _interior(a)
+    exp_a = (math.degrees(math.atan2(-0.5 * 8, 0.25 * 8)) + 360.0) % 360.0   # atan2(-X, Y), X = 8*0.5, Y = 8*0.25
+    assert float(ai.min()) == float(ai.max()) and abs(float(ai[0, 0]) - exp_a) <= 1e-4
+    del a, ai
+    # a plane has zero curvature (-0.0 like the reference's flat case)
+    c = _interior(xb.curvature(agg).data)
+    assert float(c.abs().max()) == 0.0
+    del c
+    # focal.mean: interior mean of a plane is the plane itself; window counts on the border are
+    # 6 (edges) and 4 (corners): check through the constant raster too
+    m = xb.mean(agg).data
+    assert float((_interior(m) - _interior(ramp)).abs().max()) <= 1e-3 * 1e-2   # exact up to f32 rounding of the mean
+    del m
+    ramp.fill_(7.25)
+    const = da(xb, ramp, res=(30.0, 30.0))
+    m = xb.mean(const).data
+    assert float(m.min()) == 7.25 and float(m.max()) == 7.25          # idempotent on constants, clamped edges
+    del m
+    h = _interior(xb.hillshade(const).data)
+    flat = 0.5 * (math.sin(math.radians(25)) + 1.0)
+    assert float(h.min()) == float(h.max()) and abs(float(h[0, 0]) - flat) < 1e-6
+    del h
+    # partition invariance at full size: rows [a, b) of the whole-raster result == the result of
+    # the stripe [a-1, b+1) computed on its own
+    ramp.copy_(torch.sin(xs * 0.001) * 400 + torch.cos(ys * 0.0007) * 300 + 0.01 * ((xs * 7 + ys * 13) % 97))
+    whole = xb.slope(agg).data
+    a0, b0 = H // 2 - 1000, H // 2 + 1000
+    part = xb.slope(da(xb, ramp[a0 - 1:b0 + 1], res=(30.0, 30.0))).data[1:-1]
+    assert bool(torch.equal(torch.nan_to_num(whole[a0:b0], nan=-5.0), torch.nan_to_num(part, nan=-5.0)))
+
+
+def test_hotspots_vs_reference_outputs(xb, refout):
+    r = refout
+    agg = da(xb, dev(r["hotspots.dem"]))
+    out = xb.hotspots(agg, r["hotspots.kernel"])
+    assert out.attrs["unit"] == "%" and out.data.dtype == torch.int8
+    np.testing.assert_array_equal(host(out), r["hotspots.out"])
+    np.testing.assert_array_equal(host(xb.hotspots(agg, np.ones((5, 5)))), r["hotspots.out_5x5"])
+    outh = xb.hotspots(da(xb, r["hotspots.dem"]), r["hotspots.kernel"]).data     # numpy in -> numpy out
+    assert isinstance(outh, np.ndarray) and outh.dtype == np.int8
+    np.testing.assert_array_equal(outh, r["hotspots.out"])
+    with pytest.raises(ZeroDivisionError):                                        # test_focal.py:457-463
+        xb.hotspots(da(xb, dev(np.zeros((10, 12), np.float32))), np.ones((3, 3)))
+
+
+def test_crosstab_vs_reference_outputs(xb, refout):
+    r = refout
+    zones, values = da(xb, dev(r["crosstab.zones"])), da(xb, dev(r["crosstab.values"]))
+    for agg_name in ("count", "percentage"):
+        df = xb.zonal_crosstab(zones, values, agg=agg_name)
+        np.testing.assert_array_equal(np.asarray([float(c) for c in df.columns[1:]]), r["crosstab.%s.columns" % agg_name])
+        np.testing.assert_allclose(np.asarray(df.values, dtype=np.float64), r["crosstab.%s.table" % agg_name],
+                                   rtol=1e-6, equal_nan=True)
+    df = xb.zonal_crosstab(zones, values, zone_ids=[1, 3, 9], cat_ids=[11.0, 13.0], nodata_values=12.0)
+    np.testing.assert_array_equal(np.asarray(df.values, dtype=np.float64), r["crosstab.sub.table"])
+    with pytest.raises(ValueError):
+        xb.zonal_crosstab(zones, values, agg="median")

@@ -210,3 +210,24 @@ def test_threads_do_not_change_results(refout):
     z = refout["dem.smooth"]
     np.testing.assert_array_equal(o.slope(z, 30, 30, nthreads=4), o.slope(z, 30, 30))
     np.testing.assert_array_equal(o.focal_mean(z, nthreads=4), o.focal_mean(z))
+
+
+def test_hotspots_vs_reference(refout):
+    r = refout
+    np.testing.assert_array_equal(o.hotspots(r["hotspots.dem"], r["hotspots.kernel"]), r["hotspots.out"])
+    np.testing.assert_array_equal(o.hotspots(r["hotspots.dem"], np.ones((5, 5))), r["hotspots.out_5x5"])
+    assert set(np.unique(r["hotspots.out"])) - {0} != set()      # the fixture really has hot / cold cells
+
+
+def test_crosstab_vs_reference(refout):
+    r = refout
+    for agg in ("count", "percentage"):
+        res = o.crosstab(r["crosstab.zones"], r["crosstab.values"], agg=agg)
+        cols = [c for c in res if not isinstance(c, str)]
+        np.testing.assert_array_equal(np.asarray(cols, dtype=np.float64), r["crosstab.%s.columns" % agg])
+        table = np.column_stack([res["zone"]] + [res[c] for c in cols]).astype(np.float64)
+        np.testing.assert_allclose(table, r["crosstab.%s.table" % agg], rtol=1e-6, equal_nan=True)
+    res = o.crosstab(r["crosstab.zones"], r["crosstab.values"], zone_ids=[1, 3, 9], cat_ids=[11.0, 13.0],
+                     nodata_values=12.0)
+    table = np.column_stack([res["zone"], res[11.0], res[13.0]]).astype(np.float64)
+    np.testing.assert_array_equal(table, r["crosstab.sub.table"])

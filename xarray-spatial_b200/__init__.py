@@ -10,10 +10,11 @@ from .aspect import aspect  # noqa: F401
 from .convolution import convolution_2d, convolve_2d  # noqa: F401
 from .curvature import curvature  # noqa: F401
 from .focal import apply as focal_apply  # noqa: F401
-from .focal import focal_stats, mean  # noqa: F401
+from .focal import focal_stats, hotspots, mean  # noqa: F401
 from .hillshade import hillshade  # noqa: F401
 from .multispectral import arvi, ebbi, evi, gci, nbr, nbr2, ndmi, ndvi, savi, sipi  # noqa: F401
 from .slope import slope  # noqa: F401
+from .zonal import crosstab as zonal_crosstab  # noqa: F401
 from .zonal import stats as zonal_stats  # noqa: F401
 
 __version__ = "0.1.0"

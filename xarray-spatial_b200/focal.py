@@ -2,7 +2,7 @@
 
 `apply` accepts the built-in reducers only (`_calc_mean`, `_calc_sum`, ... or their names): an
 arbitrary Python/Numba callable cannot cross the C ABI.
-`hotspots` is outside the hot path.
+`hotspots` = convolve_2d + global mean/std + an int8 classification.
 """
 import ctypes
 
@@ -152,3 +152,63 @@ def focal_stats(agg, kernel, stats_funcs=['mean', 'max', 'min', 'range', 'std', 
             raise ValueError("unknown focal statistic %r" % (stats,))
         stats_aggs.append(apply(agg, kernel, func=_REDUCERS[stats]))
     return concat(stats_aggs, pd.Index(stats_funcs, name='stats', dtype=object))
+
+
+# ----------------------------------------------------------------------------- hotspots
+def _hotspots_device(data, kernel):
+    """convolve with kernel / kernel.sum(), z-score against the raster's global NaN-skipping
+    mean / std, classify (replaces focal.py:918-937 `_hotspots_numpy` / :1025 `_hotspots_cupy`)."""
+    import torch
+    from .convolution import _convolve_2d_cupy
+    from .utils import device_f32_2d, stream_ptr
+    t = device_f32_2d(data)
+    k = np.asarray(kernel, dtype=np.float64)
+    mean_array = as_device_tensor(_convolve_2d_cupy(t, k / k.sum()))
+    part = torch.empty(3, dtype=torch.float64, device=t.device)
+    tc = t.contiguous()
+    flat = tc.reshape(-1)
+    step = max(1, flat.numel() // 65536)
+    sample = flat[::step]
+    sample = sample[~torch.isnan(sample)]
+    pivot = float(sample.double().mean().item()) if sample.numel() else 0.0
+    with torch.cuda.device(t.device):
+        _lib.call("xrs_global_stats_f32", ctypes.c_void_p(tc.data_ptr()), tc.numel(), pivot,
+                  ctypes.c_void_p(part.data_ptr()), stream_ptr(tc))
+    cnt, s1, s2 = [float(x) for x in part.cpu().numpy()]
+    if cnt == 0:
+        gmean = gstd = float("nan")
+    else:
+        gmean = pivot + s1 / cnt
+        gstd = float(np.sqrt(max(s2 / cnt - (s1 / cnt) ** 2, 0.0)))
+    if gstd == 0:
+        raise ZeroDivisionError("Standard deviation of the input raster values is 0.")
+    out = torch.empty(tuple(t.shape), dtype=torch.int8, device=t.device)
+    m = mean_array.contiguous()
+    with torch.cuda.device(t.device):
+        _lib.call("xrs_hotspots_classify_f32", ctypes.c_void_p(m.data_ptr()), m.numel(), float(np.float32(gmean)),
+                  float(np.float32(gstd)), ctypes.c_void_p(out.data_ptr()), stream_ptr(m))
+    return out
+
+
+def hotspots(raster, kernel):
+    """Getis-Ord Gi* hot / cold spots: int8 confidence levels in {0, +-90, +-95, +-99}
+    (focal.py:1050-1125)."""
+    import copy
+    if not isinstance(raster, DataArray):
+        raise TypeError("`raster` must be instance of DataArray")
+    if raster.ndim != 2:
+        raise ValueError("`raster` must be 2D")
+    kind = getattr(raster.data.dtype, "kind", None)
+    if kind is not None and kind not in "iuf":
+        raise ValueError("data type must be integer or float")
+    if isinstance(raster.data, np.ndarray):
+        import torch
+        out = _hotspots_device(torch.from_numpy(np.ascontiguousarray(raster.data, dtype=np.float32)).cuda(), kernel)
+        out = out.cpu().numpy()
+    elif is_device_array(raster.data):
+        out = like_container(_hotspots_device(raster.data, kernel), raster.data)
+    else:
+        raise TypeError("Unsupported Array Type: {}".format(type(raster.data)))
+    attrs = copy.deepcopy(raster.attrs)
+    attrs['unit'] = '%'
+    return DataArray(out, coords=raster.coords, dims=raster.dims, attrs=attrs)

@@ -104,9 +104,9 @@ def hash_partials(zones_t, values_t, nodata_values=None, comm=None, cap=1 << 16)
     return ids[order], {n: a[order] for n, a in part.items()}, pivot
 
 
-def majority_by_zone(zones_t, values_t, nodata_values=None, comm=None, cap=1 << 20):
-    """dict zone id -> majority value (most frequent valid value, smallest on ties): one pass of
-    xrs_zonal_pair_count over (int32 zone, float32 value) pairs, then a tiny host group-by."""
+def pair_counts(zones_t, values_t, nodata_values=None, comm=None, cap=1 << 20):
+    """(zone ids int64, values float64, counts int64) of every distinct valid (zone, value) pair:
+    one pass of xrs_zonal_pair_count over (int32 zone, float32 value) pairs."""
     import torch
     dev = values_t.device
     if zones_t.dtype != torch.int32:
@@ -157,6 +157,12 @@ def majority_by_zone(zones_t, values_t, nodata_values=None, comm=None, cap=1 << 
         c = np.bincount(inv, weights=c).astype(np.int64)
     zone = (k >> 32).astype(np.int64)
     val = (k & 0xFFFFFFFF).astype(np.uint32).view(np.float32).astype(np.float64)
+    return zone, val, c
+
+
+def majority_by_zone(zones_t, values_t, nodata_values=None, comm=None):
+    """dict zone id -> majority value (most frequent valid value, smallest on ties)."""
+    zone, val, c = pair_counts(zones_t, values_t, nodata_values, comm)
     order = np.lexsort((val, -c, zone))      # per zone: highest count first, then smallest value
     zone, val = zone[order], val[order]
     first = np.r_[True, zone[1:] != zone[:-1]]
@@ -379,3 +385,70 @@ def stats(zones, values, zone_ids=None,
         coords.update(values.coords)
         return DataArray(result, coords=coords, dims=('stats',) + tuple(values.dims), attrs=values.attrs)
     return result
+
+
+TOTAL_COUNT = '_total_count'
+
+
+def crosstab(zones, values, zone_ids=None, cat_ids=None, layer=None, agg="count", nodata_values=None, comm=None):
+    """Cross-tabulated cell counts (or percentages) of the categories of a 2-D `values` raster
+    per zone (zonal.py:922-1155, 2-D case): DataFrame with a `zone` column and one column per
+    category.  Built on the (zone, value) pair histogram of xrs_zonal_pair_count."""
+    if not isinstance(zones, DataArray):
+        raise TypeError("zones must be instance of DataArray")
+    if not isinstance(values, DataArray):
+        raise TypeError("values must be instance of DataArray")
+    if zones.ndim != 2:
+        raise ValueError("zones must be 2D")
+    if values.ndim not in (2, 3):
+        raise ValueError("`values` must use either 2D or 3D coordinates.")
+    if values.ndim == 3:
+        raise NotImplementedError("3-D `values` are not supported by the B200 backend")
+    validate_arrays(zones, values)
+    if agg not in ("percentage", "count"):
+        raise ValueError("`agg` method for 2D data array must be one of following ['percentage', 'count']")
+    import torch
+    if isinstance(values.data, np.ndarray):
+        zt = torch.from_numpy(np.ascontiguousarray(zones.data)).cuda()
+        vt = torch.from_numpy(np.ascontiguousarray(values.data)).cuda()
+    else:
+        zt, vt = as_device_tensor(zones.data), as_device_tensor(values.data)
+    zt = _prepare(zt, (torch.int32, torch.int64, torch.float32, torch.float64))
+    vt_f = vt.contiguous() if vt.dtype in (torch.float32, torch.float64) else vt.to(torch.float64)
+    unique_zones, _, _ = hash_partials(zt, vt_f, None, comm=comm)
+    pz, pv, pc = pair_counts(zt, vt_f, nodata_values, comm=comm)
+    vdtype = np.dtype(str(vt.dtype).replace("torch.", "")) if not isinstance(values.data, np.ndarray) else values.data.dtype
+    unique_cats = np.unique(pv).astype(vdtype)
+    if cat_ids is None:
+        cats = unique_cats
+    else:
+        cats = [c for c in cat_ids if c in unique_cats]
+    if zone_ids is None:
+        sel = unique_zones
+    else:
+        sel = np.array([z for z in zone_ids if z in unique_zones], dtype=unique_zones.dtype)
+    zpos = {float(z): i for i, z in enumerate(sel)}
+    cats = sorted(cats)
+    table = {c: np.zeros(len(sel), dtype=np.int64) for c in cats}
+    total = np.zeros(len(sel), dtype=np.float32)
+    bounds = np.asarray([float(c) for c in cats], dtype=np.float64)
+    for z, v, c in zip(pz.tolist(), pv.tolist(), pc.tolist()):
+        i = zpos.get(float(z))
+        if i is None:
+            continue
+        total[i] += c
+        # zonal.py:719-727: a selected category also collects the unselected categories between it
+        # and the previous selected one (the reference's `cat_start` only advances at selected
+        # categories); with cat_ids=None this is the plain per-category count
+        j = int(np.searchsorted(bounds, v, side="left"))
+        if j < len(cats):
+            table[cats[j]][i] += c
+    d = {"zone": sel}
+    if agg == "percentage":
+        total[total == 0] = np.nan
+        for c in cats:
+            d[c] = table[c] / total * 100
+    else:
+        for c in cats:
+            d[c] = table[c]
+    return pd.DataFrame(d)
