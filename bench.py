@@ -259,10 +259,15 @@ def run_gpu_arm(args):
     rows_launch = hp  # the kernel processes the padded stripe
     alg_bytes = ALG_BYTES_PER_CELL * rows_launch * W
     achieved = alg_bytes / (kmean[dom] * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu capture
+    # (profiles/r01_bench_ncu_summary.md, taken on a 32768 x 32768 launch), scaled to the rows of
+    # this launch
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
             traffic = json.load(f).get(names[dom])
+        if traffic is not None:
+            traffic = traffic * (float(rows_launch) * W) / (32768.0 * 32768.0)
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",

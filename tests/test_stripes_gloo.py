@@ -54,6 +54,18 @@ def _worker(rank, world, port, H, W, radius, q):
             dist.all_reduce(t, op=op)
         cols = zonal.finalize(dict(count=cnt.numpy(), s1=s1.numpy(), s2=s2.numpy(), min=mn.numpy(), max=mx.numpy()),
                               np.full(len(ids), piv), ["mean", "var", "count", "min", "max", "sum"])
+        # the product's own combiner: per-stripe tables with DIFFERENT id sets -> all-gather of
+        # the ids + dense AllReduce (zonal.allreduce_tables)
+        present = np.unique(zones)
+        loc = dict(count=np.array([(zones == z).sum() for z in present], dtype=np.int64),
+                   s1=np.array([(vals[zones == z] - piv).sum() for z in present]),
+                   s2=np.array([((vals[zones == z] - piv) ** 2).sum() for z in present]),
+                   min=np.array([vals[zones == z].min() for z in present]),
+                   max=np.array([vals[zones == z].max() for z in present]))
+        uids, upart = zonal.allreduce_tables(present, loc, torch.device("cpu"), dist.group.WORLD)
+        ok_tab = bool(np.array_equal(uids, ids) and np.array_equal(upart["count"], cnt.numpy())
+                      and np.allclose(upart["s1"], s1.numpy()) and np.allclose(upart["s2"], s2.numpy())
+                      and np.array_equal(upart["min"], mn.numpy()) and np.array_equal(upart["max"], mx.numpy()))
         allv = (full % 17).double().numpy()
         allz = (np.arange(H)[:, None] // 3) * 2 + (np.arange(W)[None, :] // (W // 2))
         ok_z = True
@@ -62,7 +74,7 @@ def _worker(rank, world, port, H, W, radius, q):
             ok_z &= bool(np.isclose(cols["mean"][i], v.mean()) and np.isclose(cols["var"][i], v.var())
                          and cols["count"][i] == v.size and cols["min"][i] == v.min() and cols["max"][i] == v.max()
                          and np.isclose(cols["sum"][i], v.sum()))
-        q.put((rank, ok_halo, ok_z, (st.y0, st.y1, st.top, st.bot)))
+        q.put((rank, ok_halo, ok_z and ok_tab, (st.y0, st.y1, st.top, st.bot)))
     finally:
         dist.destroy_process_group()
 

@@ -6,8 +6,8 @@ import numpy as np
 
 from . import _lib
 from ._xr import DataArray, Dataset
-from .utils import (as_device_tensor, device_f32_2d, get_dataarray_resolution, is_device_array,
-                    like_container, stream_ptr)
+from .utils import (device_f32_2d, get_dataarray_resolution, is_device_array, like_container,
+                    stream_ptr)
 
 
 def surface_suite(agg, azimuth=225, angle_altitude=25, products=("slope", "aspect", "curvature", "hillshade")):

@@ -105,27 +105,49 @@ template <typename VT> __device__ __forceinline__ void zh_reset(ZhRun &r) {
     r.mnd = INFINITY; r.mxd = -INFINITY;
 }
 
+// finite and != nodata (zonal.py:159).  The nodata comparison happens in the values' dtype, like
+// NumPy's `zone_values != nodata_values` with a Python scalar.
+template <typename VT> __device__ __forceinline__ bool zh_valid(VT v, const ZhArgs &a) {
+    if constexpr (sizeof(VT) == 4) return (fabsf(v) <= 3.402823466e38f) && !(a.has_nodata && v == (float)a.nodata);
+    else return (fabs(v) <= 1.7976931348623157e308) && !(a.has_nodata && v == a.nodata);
+}
+
 template <typename VT> __device__ __forceinline__ void zh_add(ZhRun &r, VT v, const ZhArgs &a) {
-    if constexpr (sizeof(VT) == 4) {
-        const bool ok = (fabsf(v) <= 3.402823466e38f) && !(a.has_nodata && (double)v == a.nodata);
-        if (ok) {
-            const double d = (double)v - a.pivot;
-            r.s1 += d;
-            r.s2 = fma(d, d, r.s2);
+    if (zh_valid<VT>(v, a)) {
+        const double d = (double)v - a.pivot;
+        r.s1 += d;
+        r.s2 = fma(d, d, r.s2);
+        if constexpr (sizeof(VT) == 4) {
             r.mnf = fminf(r.mnf, v);
             r.mxf = fmaxf(r.mxf, v);
-            r.cnt += 1u;
-        }
-    } else {
-        const bool ok = (fabs(v) <= 1.7976931348623157e308) && !(a.has_nodata && v == a.nodata);
-        if (ok) {
-            const double d = v - a.pivot;
-            r.s1 += d;
-            r.s2 = fma(d, d, r.s2);
+        } else {
             r.mnd = fmin(r.mnd, v);
             r.mxd = fmax(r.mxd, v);
-            r.cnt += 1u;
         }
+        r.cnt += 1u;
+    }
+}
+
+// four cells of one zone at once, branch-free, with short dependency chains (tree sums)
+template <typename VT> __device__ __forceinline__ void zh_add4(ZhRun &r, const VT (&v)[4], const ZhArgs &a) {
+    bool ok[4];
+    double d[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        ok[k] = zh_valid<VT>(v[k], a);
+        d[k] = ok[k] ? (double)v[k] - a.pivot : 0.0;
+    }
+    r.s1 += (d[0] + d[1]) + (d[2] + d[3]);
+    r.s2 += fma(d[0], d[0], d[1] * d[1]) + fma(d[2], d[2], d[3] * d[3]);
+    r.cnt += (unsigned)ok[0] + (unsigned)ok[1] + (unsigned)ok[2] + (unsigned)ok[3];
+    if constexpr (sizeof(VT) == 4) {
+        const float inf = INFINITY;
+        r.mnf = fminf(r.mnf, fminf(fminf(ok[0] ? v[0] : inf, ok[1] ? v[1] : inf), fminf(ok[2] ? v[2] : inf, ok[3] ? v[3] : inf)));
+        r.mxf = fmaxf(r.mxf, fmaxf(fmaxf(ok[0] ? v[0] : -inf, ok[1] ? v[1] : -inf), fmaxf(ok[2] ? v[2] : -inf, ok[3] ? v[3] : -inf)));
+    } else {
+        const double inf = INFINITY;
+        r.mnd = fmin(r.mnd, fmin(fmin(ok[0] ? v[0] : inf, ok[1] ? v[1] : inf), fmin(ok[2] ? v[2] : inf, ok[3] ? v[3] : inf)));
+        r.mxd = fmax(r.mxd, fmax(fmax(ok[0] ? v[0] : -inf, ok[1] ? v[1] : -inf), fmax(ok[2] ? v[2] : -inf, ok[3] ? v[3] : -inf)));
     }
 }
 
@@ -150,7 +172,7 @@ template <typename T> __device__ __forceinline__ ZhQuad<T> zh_load(const T *p, i
 }
 
 template <typename VT, typename ZT>
-__global__ void __launch_bounds__(kZhThreads) zonal_hash_kernel(const __grid_constant__ ZhArgs a) {
+__global__ void __launch_bounds__(kZhThreads, 3) zonal_hash_kernel(const __grid_constant__ ZhArgs a) {
     __shared__ long long s_keys[kZhLocalCap];
     __shared__ double s_s1[kZhLocalCap], s_s2[kZhLocalCap], s_mn[kZhLocalCap], s_mx[kZhLocalCap];
     __shared__ unsigned s_cnt[kZhLocalCap];
@@ -246,19 +268,31 @@ __global__ void __launch_bounds__(kZhThreads) zonal_hash_kernel(const __grid_con
         const int64_t x = strip * 128 + 4 * lane;
         const int64_t y0 = seg * kZhSegRows, y1 = min(y0 + (int64_t)kZhSegRows, H);
         const int nv = (int)max((int64_t)0, min((int64_t)4, a.W - x));
-        for (int64_t y = y0; y < y1; y += kZhUnroll) {
+        // whole strip inside the raster, 16-byte aligned rows: plain 128-bit loads, no bounds logic
+        const bool strip_fast = row_vec && (strip * 128 + 128 <= a.W);
+        const VT *vrow = values + y0 * a.W + x;
+        const ZT *zrow = zones + y0 * a.W + x;
+        for (int64_t y = y0; y < y1; y += kZhUnroll, vrow += kZhUnroll * a.W, zrow += kZhUnroll * a.W) {
             ZhQuad<VT> v[kZhUnroll];
             ZhQuad<ZT> z[kZhUnroll];
+            const bool batch_fast = strip_fast && (y + kZhUnroll <= y1);
+            if (batch_fast) {
 #pragma unroll
-            for (int u = 0; u < kZhUnroll; ++u) {
-                const int64_t i0 = (y + u) * a.W + x;
-                const int nvu = (y + u < y1) ? nv : 0;
-                v[u] = zh_load<VT>(values, i0, i0 + nvu, row_vec);
-                z[u] = zh_load<ZT>(zones, i0, i0 + nvu, row_vec);
+                for (int u = 0; u < kZhUnroll; ++u) {
+                    v[u] = zh_load<VT>(vrow + u * a.W, 0, 4, true);
+                    z[u] = zh_load<ZT>(zrow + u * a.W, 0, 4, true);
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < kZhUnroll; ++u) {
+                    const int nvu = (y + u < y1) ? nv : 0;
+                    v[u] = zh_load<VT>(vrow + u * a.W, 0, nvu, row_vec);
+                    z[u] = zh_load<ZT>(zrow + u * a.W, 0, nvu, row_vec);
+                }
             }
 #pragma unroll
             for (int u = 0; u < kZhUnroll; ++u) {
-                const int nvu = (y + u < y1) ? nv : 0;
+                const int nvu = batch_fast ? 4 : ((y + u < y1) ? nv : 0);
                 const bool same = have && (z[u].v[0] == cur_z) && (z[u].v[1] == cur_z) &&
                                   (z[u].v[2] == cur_z) && (z[u].v[3] == cur_z);
                 const bool fast = (nvu == 4) && same;
@@ -279,8 +313,7 @@ __global__ void __launch_bounds__(kZhThreads) zonal_hash_kernel(const __grid_con
                         if (live && cur_ok) zh_add<VT>(run, v[u].v[k], a);
                     }
                 } else if (fast && cur_ok) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) zh_add<VT>(run, v[u].v[k], a);
+                    zh_add4<VT>(run, v[u].v, a);
                 }
             }
         }
@@ -399,7 +432,10 @@ __global__ void zonal_hash_init_kernel(long long *keys, unsigned long long *coun
 template <typename VT, typename ZT> static int launch_zh(const ZhArgs &a, cudaStream_t s) {
     const int64_t H = a.n / a.W;
     const int64_t n_tasks = ((a.W + 127) / 128) * ((H + kZhSegRows - 1) / kZhSegRows);
-    int64_t grid = (int64_t)sm_count() * 4;
+    int per_sm = 0;
+    XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zonal_hash_kernel<VT, ZT>, kZhThreads, 0));
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)sm_count() * per_sm;
     const int64_t need = (n_tasks + kZhThreads / 32 - 1) / (kZhThreads / 32);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;

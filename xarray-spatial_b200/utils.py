@@ -13,7 +13,6 @@ import os
 import numpy as np
 
 from . import _lib
-from ._xr import DataArray
 
 try:
     import torch

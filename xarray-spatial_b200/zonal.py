@@ -12,12 +12,11 @@ import pandas as pd
 
 from . import _lib
 from ._xr import DataArray, Dataset
-from .utils import (ArrayTypeFunctionMapping, as_device_tensor, is_device_array, like_container,
-                    stream_ptr, validate_arrays)
+from .utils import (ArrayTypeFunctionMapping, as_device_tensor, like_container, stream_ptr,
+                    validate_arrays)
 
 _DEFAULT_STATS = ("mean", "max", "min", "sum", "std", "var", "count", "majority")
 _PARTIAL_STATS = ("mean", "max", "min", "sum", "std", "var", "count")
-_TORCH_DT = None
 
 
 def _dtype_code(t):
@@ -41,13 +40,14 @@ _EMPTY_KEY = -(1 << 63)
 
 
 def _sample_pivot(values_t, comm=None):
-    """One global shift p keeps sum((v-p)^2) well conditioned; a strided sample is enough."""
+    """One global shift p keeps sum((v-p)^2) well conditioned; the mean of a small strided sample
+    is enough (one tiny device-to-host copy)."""
     import torch
     flat = values_t.reshape(-1)
-    step = max(1, flat.numel() // 65536)
-    sample = flat[::step].to(torch.float64)
-    sample = sample[torch.isfinite(sample)]
-    p0 = float(sample.mean().item()) if sample.numel() else 0.0
+    step = max(1, flat.numel() // 4096)
+    sample = flat[::step][:4096].to(torch.float64).cpu().numpy()
+    sample = sample[np.isfinite(sample)]
+    p0 = float(sample.mean()) if sample.size else 0.0
     if comm is not None:
         import torch.distributed as dist
         pt = torch.tensor([p0], dtype=torch.float64, device=values_t.device)
@@ -67,39 +67,35 @@ def hash_partials(zones_t, values_t, nodata_values=None, comm=None, cap=1 << 16)
     pivot = _sample_pivot(values_t, comm)
     P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
     while True:
-        keys = torch.empty(cap, dtype=torch.int64, device=dev)
-        count = torch.empty(cap, dtype=torch.int64, device=dev)
-        s1 = torch.empty(cap, dtype=torch.float64, device=dev)
-        s2 = torch.empty(cap, dtype=torch.float64, device=dev)
-        vmin = torch.empty(cap, dtype=torch.float64, device=dev)
-        vmax = torch.empty(cap, dtype=torch.float64, device=dev)
+        # one blob: rows = keys, count (int64 bit patterns), s1, s2, min, max; + the overflow flag
+        blob = torch.empty((6, cap), dtype=torch.float64, device=dev)
         ovf = torch.empty(1, dtype=torch.int32, device=dev)
+        keys, count = blob[0].view(torch.int64), blob[1].view(torch.int64)
         with torch.cuda.device(dev):
             st = stream_ptr(values_t)
-            _lib.call("xrs_zonal_hash_init", P(keys), P(count), P(s1), P(s2), P(vmin), P(vmax), cap, P(ovf), st)
+            _lib.call("xrs_zonal_hash_init", P(keys), P(count), P(blob[2]), P(blob[3]), P(blob[4]), P(blob[5]), cap,
+                      P(ovf), st)
             _lib.call("xrs_zonal_hash_accumulate", P(values_t), _dtype_code(values_t), P(zones_t),
                       _dtype_code(zones_t), values_t.numel(), int(values_t.shape[-1]) if values_t.dim() else 1,
                       pivot, 0 if nodata_values is None else 1,
                       0.0 if nodata_values is None else float(nodata_values),
-                      P(keys), P(count), P(s1), P(s2), P(vmin), P(vmax), cap, P(ovf), st)
+                      P(keys), P(count), P(blob[2]), P(blob[3]), P(blob[4]), P(blob[5]), cap, P(ovf), st)
+        used = torch.nonzero(keys != _EMPTY_KEY).reshape(-1)
+        packed = blob[:, used].cpu().numpy()          # the only sizeable device-to-host copy (6 x zones)
         if int(ovf.item()) == 0:
             break
         if cap >= (1 << 24):
             raise NotImplementedError("more than 16M distinct zones are not supported")
         cap *= 16
-    used = torch.nonzero(keys != _EMPTY_KEY).reshape(-1)
-    k = keys[used].cpu().numpy()
-    part = dict(count=count[used].cpu().numpy(), s1=s1[used].cpu().numpy(), s2=s2[used].cpu().numpy(),
-                min=vmin[used].cpu().numpy(), max=vmax[used].cpu().numpy())
+    k = packed[0].view(np.int64)
+    part = dict(count=packed[1].view(np.int64).copy(), s1=packed[2].copy(), s2=packed[3].copy(),
+                min=packed[4].copy(), max=packed[5].copy())
     if zones_t.dtype.is_floating_point:
         ids = k.view(np.float64).astype(np.float32 if zones_t.dtype == torch.float32 else np.float64)
     else:
         ids = k.astype(np.int32 if zones_t.dtype == torch.int32 else np.int64)
     if comm is not None:
-        import torch.distributed as dist
-        gathered = [None] * dist.get_world_size(comm)
-        dist.all_gather_object(gathered, (ids, part), group=comm)
-        ids, part = merge_tables(gathered)
+        ids, part = allreduce_tables(ids, part, dev, comm)
     order = np.argsort(ids, kind="stable")
     return ids[order], {n: a[order] for n, a in part.items()}, pivot
 
@@ -167,6 +163,43 @@ def majority_by_zone(zones_t, values_t, nodata_values=None, comm=None):
     zone, val = zone[order], val[order]
     first = np.r_[True, zone[1:] != zone[:-1]]
     return dict(zip(zone[first].tolist(), val[first].tolist()))
+
+
+def allreduce_tables(ids, part, dev, comm):
+    """Combine the per-stripe tables of all ranks: the id lists are all-gathered (a few KB), every
+    rank scatters its partials into dense arrays over the sorted union of ids, and the dense
+    arrays are combined with NCCL AllReduce (SUM for count / sums, MIN, MAX) -- SURVEY.md 8e."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(comm)
+    n_local = torch.tensor([len(ids)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=comm)
+    nmax = int(max(int(c.item()) for c in counts))
+    pad = np.zeros(nmax, dtype=np.float64)
+    pad[:len(ids)] = np.asarray(ids, dtype=np.float64)
+    mine = torch.as_tensor(pad, device=dev)
+    gathered = [torch.empty(nmax, dtype=torch.float64, device=dev) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=comm)
+    union = np.unique(np.concatenate([g[:int(c.item())].cpu().numpy() for g, c in zip(gathered, counts)]))
+    pos = np.searchsorted(union, np.asarray(ids, dtype=np.float64))
+    nz = len(union)
+    dense = dict(count=torch.zeros(nz, dtype=torch.int64, device=dev),
+                 s1=torch.zeros(nz, dtype=torch.float64, device=dev),
+                 s2=torch.zeros(nz, dtype=torch.float64, device=dev),
+                 min=torch.full((nz,), float("inf"), dtype=torch.float64, device=dev),
+                 max=torch.full((nz,), float("-inf"), dtype=torch.float64, device=dev))
+    if len(ids):
+        idx = torch.as_tensor(pos, device=dev)
+        for k in dense:
+            dense[k][idx] = torch.as_tensor(part[k], device=dev)
+    if nz:
+        dist.all_reduce(dense["count"], op=dist.ReduceOp.SUM, group=comm)
+        dist.all_reduce(dense["s1"], op=dist.ReduceOp.SUM, group=comm)
+        dist.all_reduce(dense["s2"], op=dist.ReduceOp.SUM, group=comm)
+        dist.all_reduce(dense["min"], op=dist.ReduceOp.MIN, group=comm)
+        dist.all_reduce(dense["max"], op=dist.ReduceOp.MAX, group=comm)
+    return union.astype(np.asarray(ids).dtype), {k: v.cpu().numpy() for k, v in dense.items()}
 
 
 def merge_tables(tables):
