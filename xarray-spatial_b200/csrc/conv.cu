@@ -50,17 +50,21 @@ __device__ __forceinline__ void load_tile_tma(const CUtensorMap *tmap, float *ti
 }
 
 // ----------------------------------------------------------------------------- convolve
+// 128 x 64 output tile per CTA, 256 threads = 16 (x) x 16 (y); a thread owns 4 rows x (4 + 4)
+// columns: columns 4tx .. 4tx+3 and 64+4tx .. 64+4tx+3, so that consecutive lanes read
+// consecutive 16-byte pieces of a shared-memory row (conflict-free LDS.128).  The float32 tile
+// is read directly and widened in registers (16 F2F per 128 DFMA); 32 independent float64
+// accumulators per thread give the FP64 pipe enough parallelism at 2-3 CTAs per SM.
+constexpr int kConvTileH = 64;
+
 __global__ void __launch_bounds__(256)
 conv2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ConvWeights cw,
               float *__restrict__ out, int64_t out_pitch_elems, const TileGeom g) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int nbox = (g.sh + g.box_h - 1) / g.box_h;
     const size_t tile_cells = (size_t)nbox * g.box_h * g.sw;
-    // tile32 first: TMA destinations must be 128-byte aligned (box_h * sw * 4 is, see tile_geom)
     float *tile32 = reinterpret_cast<float *>(smem_raw);
-    const size_t off64 = (tile_cells * sizeof(float) + 127) / 128 * 128;
-    double *tile64 = reinterpret_cast<double *>(smem_raw + off64);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + off64 + tile_cells * sizeof(double));
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + tile_cells * sizeof(float));
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap);
@@ -69,41 +73,40 @@ conv2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
     }
     __syncthreads();
 
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int64_t n_tiles = (int64_t)g.tiles_x * g.tiles_y;
     uint32_t parity = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int tile_y = (int)(t / g.tiles_x), tile_x = (int)(t % g.tiles_x);
-        const int x0 = tile_x * kTileW, y0 = tile_y * kTileH;
+        const int x0 = tile_x * kTileW, y0 = tile_y * kConvTileH;
         load_tile_tma(&tmap, tile32, bar, g, x0, y0, parity);
         parity ^= 1u;
-        // widen once: f32 -> f64
-        for (size_t i = threadIdx.x; i < (size_t)g.sh * g.sw; i += blockDim.x) tile64[i] = (double)tile32[i];
-        __syncthreads();
 
-        double acc[4][4];
+        double acc[4][8];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+            for (int c = 0; c < 8; ++c) acc[r][c] = 0.0;
 
         // Input row j of the thread's window feeds output row r with kernel row ky = j - r.
-        // Rows 3 .. kh-1 feed all four output rows and chunks [off .. off+kw) that lie fully
-        // inside the kernel need no tap test: that common case is straight-line DFMA code;
-        // the (few) edge rows / edge chunks take the generic, predicated path.
+        // Rows 3 .. kh-1 feed all four output rows, and 4-tap chunks lying fully inside the
+        // kernel need no tap test: that common case is straight-line DFMA code; the few edge
+        // rows / edge chunks take the generic, predicated path.  Taps are indexed from the
+        // 16-byte aligned tile origin: tap kx sits at column kx + off.
         const int rows_in = 4 + g.kh - 1;
         const int n_taps = g.off + g.kw;
         for (int j = 0; j < rows_in; ++j) {
-            const double *rowp = tile64 + (size_t)(ty * 4 + j) * g.sw + 4 * tx;
+            const float *rowp = tile32 + (size_t)(ty * 4 + j) * g.sw + 4 * tx;
             const bool full_rows = (j >= 3) && (j < g.kh);
             for (int kb = 0; kb < n_taps; kb += 4) {
-                double v[8];
-                const double2 q0 = *reinterpret_cast<const double2 *>(rowp + kb);
-                const double2 q1 = *reinterpret_cast<const double2 *>(rowp + kb + 2);
-                const double2 q2 = *reinterpret_cast<const double2 *>(rowp + kb + 4);
-                const double2 q3 = *reinterpret_cast<const double2 *>(rowp + kb + 6);
-                v[0] = q0.x; v[1] = q0.y; v[2] = q1.x; v[3] = q1.y;
-                v[4] = q2.x; v[5] = q2.y; v[6] = q3.x; v[7] = q3.y;
+                const float4 a0 = *reinterpret_cast<const float4 *>(rowp + kb);
+                const float4 a1 = *reinterpret_cast<const float4 *>(rowp + kb + 4);
+                const float4 b0 = *reinterpret_cast<const float4 *>(rowp + 64 + kb);
+                const float4 b1 = *reinterpret_cast<const float4 *>(rowp + 64 + kb + 4);
+                const double va[8] = {(double)a0.x, (double)a0.y, (double)a0.z, (double)a0.w,
+                                      (double)a1.x, (double)a1.y, (double)a1.z, (double)a1.w};
+                const double vb[8] = {(double)b0.x, (double)b0.y, (double)b0.z, (double)b0.w,
+                                      (double)b1.x, (double)b1.y, (double)b1.z, (double)b1.w};
                 const bool full_chunk = (kb >= g.off) && (kb + 4 <= n_taps);
                 if (full_rows && full_chunk) {
                     const double *w0 = cw.w + (j * g.kw + kb - g.off);  // kernel row j, taps kb-off ..
@@ -114,7 +117,10 @@ conv2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
                         for (int tt = 0; tt < 4; ++tt) {
                             const double wv = wr[tt];
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) acc[r][c] = fma(wv, v[c + tt], acc[r][c]);
+                            for (int c = 0; c < 4; ++c) {
+                                acc[r][c] = fma(wv, va[c + tt], acc[r][c]);
+                                acc[r][4 + c] = fma(wv, vb[c + tt], acc[r][4 + c]);
+                            }
                         }
                     }
                 } else {
@@ -128,7 +134,10 @@ conv2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
                                 if (kx >= 0 && kx < g.kw) {
                                     const double wv = cw.w[ky * g.kw + kx];
 #pragma unroll
-                                    for (int c = 0; c < 4; ++c) acc[r][c] = fma(wv, v[c + tt], acc[r][c]);
+                                    for (int c = 0; c < 4; ++c) {
+                                        acc[r][c] = fma(wv, va[c + tt], acc[r][c]);
+                                        acc[r][4 + c] = fma(wv, vb[c + tt], acc[r][4 + c]);
+                                    }
                                 }
                             }
                         }
@@ -136,15 +145,21 @@ conv2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
                 }
             }
         }
-        const int64_t xo = (int64_t)x0 + 4 * tx;
+        const int64_t xa = (int64_t)x0 + 4 * tx, xb = xa + 64;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int64_t yo = (int64_t)y0 + ty * 4 + r;
-            if (yo < g.H && xo < g.W)  // W % 4 == 0 on this path
-                __stcs(reinterpret_cast<float4 *>(out + yo * out_pitch_elems + xo),
-                       make_float4((float)acc[r][0], (float)acc[r][1], (float)acc[r][2], (float)acc[r][3]));
+            if (yo < g.H) {  // W % 4 == 0 on this path: a float4 is all-in or all-out
+                float *orow = out + yo * out_pitch_elems;
+                if (xa < g.W)
+                    __stcs(reinterpret_cast<float4 *>(orow + xa),
+                           make_float4((float)acc[r][0], (float)acc[r][1], (float)acc[r][2], (float)acc[r][3]));
+                if (xb < g.W)
+                    __stcs(reinterpret_cast<float4 *>(orow + xb),
+                           make_float4((float)acc[r][4], (float)acc[r][5], (float)acc[r][6], (float)acc[r][7]));
+            }
         }
-        __syncthreads();  // tile buffers are reused by the next iteration
+        __syncthreads();  // the tile buffer is reused by the next iteration
     }
 }
 
@@ -383,16 +398,16 @@ static int check_common(const float *in, int64_t in_pitch, float *out, int64_t o
 }
 
 static bool tile_geom(TileGeom &g, CUtensorMap *tmap, const float *in, int64_t in_pitch, float *out,
-                      int64_t out_pitch, int64_t H, int64_t W, int kh, int kw) {
+                      int64_t out_pitch, int64_t H, int64_t W, int kh, int kw, int tile_h) {
     g.H = H; g.W = W; g.kh = kh; g.kw = kw; g.ry = kh / 2; g.rx = kw / 2;
     g.pad = (g.rx + 3) / 4 * 4;
     g.off = g.pad - g.rx;
     // the 8-wide chunk loads of the convolution reach 4*31 + 4*((off+kw-1)/4) + 7 cells into a row
     g.sw = kTileW + ((g.off + kw + 3) / 4) * 4 + 4;
-    g.sh = kTileH + kh - 1;
+    g.sh = tile_h + kh - 1;
     g.tiles_x = (int)((W + kTileW - 1) / kTileW);
-    g.tiles_y = (int)((H + kTileH - 1) / kTileH);
-    g.box_h = g.sh <= 64 ? g.sh : 48;  // 48 % 8 == 0 keeps the 2nd box 128-byte aligned
+    g.tiles_y = (int)((H + tile_h - 1) / tile_h);
+    g.box_h = g.sh <= 64 ? g.sh : 64;  // 64 % 8 == 0 keeps the following boxes 128-byte aligned
     if (g.sw > 256) return false;
     if (W % 4 != 0 || out_pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(out) & 15)) return false;
     return make_tensor_map_2d(tmap, in, in_pitch, H, W, 4, g.sw, g.box_h);
@@ -418,14 +433,14 @@ int xrs_convolve2d_f32(const float *in, int64_t in_pitch, float *out, int64_t ou
     TileGeom g;
     CUtensorMap tmap;
     const int sms = sm_count();
-    if (tile_geom(g, &tmap, in, in_pitch, out, out_pitch, H, W, kh, kw)) {
+    if (tile_geom(g, &tmap, in, in_pitch, out, out_pitch, H, W, kh, kw, kConvTileH)) {
         const int nbox = (g.sh + g.box_h - 1) / g.box_h;
         const size_t cells = (size_t)nbox * g.box_h * g.sw;
-        const size_t smem = (cells * 4 + 127) / 128 * 128 + cells * 8 + 16;
+        const size_t smem = cells * 4 + 16;
         if (smem <= 227 * 1024) {
             XRS_CUDA(cudaFuncSetAttribute(conv2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int per_sm = (int)((227 * 1024) / (smem + 1024));
-            if (per_sm > 4) per_sm = 4;
+            int per_sm = 0;
+            XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv2d_kernel, 256, smem));
             if (per_sm < 1) per_sm = 1;
             int64_t grid = (int64_t)sms * per_sm;
             const int64_t n_tiles = (int64_t)g.tiles_x * g.tiles_y;
@@ -454,7 +469,7 @@ int xrs_focal_stat_f32(const float *in, int64_t in_pitch, float *out, int64_t ou
     TileGeom g;
     CUtensorMap tmap;
     const int sms = sm_count();
-    if (tile_geom(g, &tmap, in, in_pitch, out, out_pitch, H, W, kh, kw)) {
+    if (tile_geom(g, &tmap, in, in_pitch, out, out_pitch, H, W, kh, kw, kTileH)) {
         const int nbox = (g.sh + g.box_h - 1) / g.box_h;
         const size_t smem = (size_t)nbox * g.box_h * g.sw * 4 + 16;
         if (smem <= 227 * 1024) {

@@ -202,24 +202,6 @@ def allreduce_tables(ids, part, dev, comm):
     return union.astype(np.asarray(ids).dtype), {k: v.cpu().numpy() for k, v in dense.items()}
 
 
-def merge_tables(tables):
-    """Merge [(ids, part), ...] from several stripes by zone id (sum / min / max)."""
-    all_ids = np.concatenate([t[0] for t in tables])
-    ids, inv = np.unique(all_ids, return_inverse=True)
-    out = dict(count=np.zeros(len(ids), np.int64), s1=np.zeros(len(ids)), s2=np.zeros(len(ids)),
-               min=np.full(len(ids), np.inf), max=np.full(len(ids), -np.inf))
-    off = 0
-    for tid, part in tables:
-        sl = inv[off:off + len(tid)]
-        off += len(tid)
-        np.add.at(out["count"], sl, part["count"])
-        np.add.at(out["s1"], sl, part["s1"])
-        np.add.at(out["s2"], sl, part["s2"])
-        np.minimum.at(out["min"], sl, part["min"])
-        np.maximum.at(out["max"], sl, part["max"])
-    return ids, out
-
-
 def zonal_partials(zones_t, values_t, ids, nodata_values=None, pivot=None, comm=None):
     """Run the kernel; returns dict of numpy arrays (count int64; s1, s2, min, max float64) and
     the pivot used.  ids: sorted numpy array of candidate zone ids."""
