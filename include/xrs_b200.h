@@ -82,6 +82,16 @@ int xrs_surface_suite_f32(const float *in, int64_t in_pitch, float *slope_out,
                           double cellsize_y, double azimuth, double angle_altitude,
                           xrs_stream_t s);
 
+/* slope / aspect with method='geodesic' (slope._run_cupy_geodesic slope.py:176-195,
+ * aspect._run_cupy_geodesic aspect.py:179-198; arithmetic of geodesic.py:40-231): elevation float32
+ * or float64 (elev_dtype XRS_F32 / XRS_F64), latitude / longitude in degrees as DEVICE float64
+ * arrays -- lat[H], lon[W] for a regular grid (latlon_2d = 0) or (H, W) contiguous arrays for a
+ * curvilinear one (latlon_2d = 1); z_factor converts the elevation unit to metres.  float32
+ * output: slope in degrees, or compass aspect (-1 on flats) when want_aspect != 0. */
+int xrs_geodesic(const void *elev, int elev_dtype, int64_t elev_pitch, const double *lat,
+                 const double *lon, int latlon_2d, float *out, int64_t out_pitch, int64_t H, int64_t W,
+                 double z_factor, int want_aspect, xrs_stream_t s);
+
 /* ------------------------------------------------------------------ focal / convolution */
 /* focal._mean_cupy (focal.py:135-146) / `_mean_numpy` (focal.py:44-67): ONE pass of the 3x3
  * NaN-skipping mean with clamped windows; centre cells equal (NaN-aware) to one of

@@ -273,6 +273,26 @@ def reference_outputs():
         g["crosstab.%s.table" % agg] = np.asarray(df.values, dtype=np.float64)
     df = zonal._crosstab_numpy(cz, cv, [1, 3, 9], ucats, [11.0, 13.0], 12.0, "count")
     g["crosstab.sub.table"] = np.asarray(df.values, dtype=np.float64)
+
+    # geodesic slope / aspect (geodesic.py) on a lat/lon grid near 46N, with NaNs and a flat patch
+    geod = ref_loader.load("geodesic")
+    gz = terrain(rng, 40, 52, nans=0.01).astype(np.float64)
+    gz[5:12, 5:12] = 1500.0
+    glat = np.linspace(46.5, 46.0, 40)
+    glon = np.linspace(7.0, 7.8, 52)
+    lat2 = np.broadcast_to(glat[:, None], gz.shape).copy()
+    lon2 = np.broadcast_to(glon[None, :], gz.shape).copy()
+    a2, b2 = geod.WGS84_A2, geod.WGS84_B2
+    g["geodesic.dem"], g["geodesic.lat"], g["geodesic.lon"] = gz, glat, glon
+    g["geodesic.slope"] = geod._cpu_geodesic_slope(np.stack([gz, lat2, lon2]), a2, b2, 1.0)
+    g["geodesic.aspect"] = geod._cpu_geodesic_aspect(np.stack([gz, lat2, lon2]), a2, b2, 1.0)
+    g["geodesic.slope_ft"] = geod._cpu_geodesic_slope(np.stack([gz, lat2, lon2]), a2, b2, 0.3048)
+    # curvilinear (2-D) coordinates
+    lat2c = lat2 + 0.0005 * np.sin(np.arange(52))[None, :]
+    lon2c = lon2 + 0.0007 * np.cos(np.arange(40))[:, None]
+    g["geodesic.lat2d"], g["geodesic.lon2d"] = lat2c, lon2c
+    g["geodesic.slope_2d"] = geod._cpu_geodesic_slope(np.stack([gz, lat2c, lon2c]), a2, b2, 1.0)
+    g["geodesic.aspect_2d"] = geod._cpu_geodesic_aspect(np.stack([gz, lat2c, lon2c]), a2, b2, 1.0)
     return g
 
 

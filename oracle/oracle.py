@@ -271,3 +271,15 @@ def crosstab(zones, values, zone_ids=None, cat_ids=None, agg="count", nodata_val
         else:
             res[c] = cnt
     return res
+
+
+# --------------------------------------------------------------------------- geodesic
+def geodesic(data, lat_2d, lon_2d, z_factor=1.0, aspect=False, nthreads=1):
+    """slope.py:167-173 / aspect.py:170-176 `_run_numpy_geodesic` -> geodesic.py:179-231."""
+    d = np.ascontiguousarray(data, dtype=np.float64)
+    la = np.ascontiguousarray(lat_2d, dtype=np.float64)
+    lo = np.ascontiguousarray(lon_2d, dtype=np.float64)
+    out = np.empty(d.shape, np.float32)
+    lib().xo_geodesic_f64(_p(d), _p(la), _p(lo), _p(out), _i64(d.shape[0]), _i64(d.shape[1]), _dbl(z_factor),
+                          _int(1 if aspect else 0), _int(nthreads))
+    return out

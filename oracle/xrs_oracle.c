@@ -325,6 +325,93 @@ XO_EXPORT void xo_ebbi_f32(const float *red, const float *swir, const float *tir
     }
 }
 
+/* ------------------------------------------------- geodesic slope / aspect
+ * geodesic.py:40-231: every 3x3 neighbourhood is converted from (lat, lon, elevation) to ECEF
+ * (:40-52), projected into the local East/North/Up frame of the centre cell, corrected for the
+ * Earth's curvature (u += (e^2 + n^2) / (2 R_mean)) and fitted with u = A e + B n (+ C) by
+ * centred least squares (:55-131); slope = atan(sqrt(A^2 + B^2)) in degrees (:134-145), aspect =
+ * atan2(-A, -B) folded to [0, 360), -1 when sqrt(A^2 + B^2) < 1e-7 (:148-172).  All float64;
+ * a NaN anywhere in the 3x3 elevations gives NaN; 1-cell NaN ring; float32 output.
+ * elev / lat / lon are (H, W) float64 arrays (the `stacked` channels of :179-231). */
+static void geo_ecef(double lat_rad, double lon_rad, double h, double a2, double b2, double *X, double *Y,
+                     double *Z) {
+    const double cos_lat = cos(lat_rad), sin_lat = sin(lat_rad), cos_lon = cos(lon_rad), sin_lon = sin(lon_rad);
+    const double N = a2 / sqrt(a2 * cos_lat * cos_lat + b2 * sin_lat * sin_lat);
+    *X = (N + h) * cos_lat * cos_lon;
+    *Y = (N + h) * cos_lat * sin_lon;
+    *Z = (b2 / a2 * N + h) * sin_lat;
+}
+
+static int geo_fit(const double *elev, const double *lat, const double *lon, int64_t W, int64_t y, int64_t x,
+                   double a2, double b2, double z_factor, double inv_2r, double *A, double *B) {
+    const double deg2rad = 3.141592653589793 / 180.0;
+    double ne[9], nl[9], no[9];
+    int idx = 0;
+    for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+            ne[idx] = elev[(y + dy) * W + x + dx];
+            nl[idx] = lat[(y + dy) * W + x + dx];
+            no[idx] = lon[(y + dy) * W + x + dx];
+            idx++;
+        }
+    for (int k = 0; k < 9; ++k)
+        if (ne[k] != ne[k]) return 0;
+    const double lat_c = lat[y * W + x] * deg2rad, lon_c = lon[y * W + x] * deg2rad;
+    double Xc, Yc, Zc;
+    geo_ecef(lat_c, lon_c, elev[y * W + x] * z_factor, a2, b2, &Xc, &Yc, &Zc);
+    const double cos_lat = cos(lat_c), sin_lat = sin(lat_c), cos_lon = cos(lon_c), sin_lon = sin(lon_c);
+    const double ex = -sin_lon, ey = cos_lon, ez = 0.0;
+    const double nx = -sin_lat * cos_lon, ny = -sin_lat * sin_lon, nz = cos_lat;
+    const double ux = cos_lat * cos_lon, uy = cos_lat * sin_lon, uz = sin_lat;
+    double e9[9], n9[9], u9[9];
+    for (int k = 0; k < 9; ++k) {
+        double Xk, Yk, Zk;
+        geo_ecef(nl[k] * deg2rad, no[k] * deg2rad, ne[k] * z_factor, a2, b2, &Xk, &Yk, &Zk);
+        const double dx = Xk - Xc, dy = Yk - Yc, dz = Zk - Zc;
+        const double ek = dx * ex + dy * ey + dz * ez;
+        const double nk = dx * nx + dy * ny + dz * nz;
+        double uk = dx * ux + dy * uy + dz * uz;
+        uk += (ek * ek + nk * nk) * inv_2r;
+        e9[k] = ek; n9[k] = nk; u9[k] = uk;
+    }
+    double me = 0.0, mn = 0.0, mu = 0.0;
+    for (int k = 0; k < 9; ++k) { me += e9[k]; mn += n9[k]; mu += u9[k]; }
+    const double inv9 = 1.0 / 9.0;
+    me *= inv9; mn *= inv9; mu *= inv9;
+    double See = 0.0, Snn = 0.0, Sen = 0.0, Seu = 0.0, Snu = 0.0;
+    for (int k = 0; k < 9; ++k) {
+        const double de = e9[k] - me, dn = n9[k] - mn, du = u9[k] - mu;
+        See += de * de; Snn += dn * dn; Sen += de * dn; Seu += de * du; Snu += dn * du;
+    }
+    const double det = See * Snn - Sen * Sen;
+    if (fabs(det) < 1e-30) { *A = 0.0; *B = 0.0; return 1; }
+    *A = (Seu * Snn - Snu * Sen) / det;
+    *B = (Snu * See - Seu * Sen) / det;
+    return 1;
+}
+
+XO_EXPORT void xo_geodesic_f64(const double *elev, const double *lat, const double *lon, float *out, int64_t H,
+                               int64_t W, double z_factor, int want_aspect, int nthreads) {
+    const double a2 = 6378137.0 * 6378137.0, b2 = 6356752.314245 * 6356752.314245;
+    const double inv_2r = 1.0 / (2.0 * 6370994.884953014);
+    fill_nan_f32(out, H * W);
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (int64_t y = 1; y < H - 1; ++y)
+        for (int64_t x = 1; x < W - 1; ++x) {
+            double A, B;
+            if (!geo_fit(elev, lat, lon, W, y, x, a2, b2, z_factor, inv_2r, &A, &B)) continue;  /* NaN */
+            if (!want_aspect) {
+                out[y * W + x] = (float)(atan(sqrt(A * A + B * B)) * (180.0 / 3.141592653589793));
+            } else {
+                if (sqrt(A * A + B * B) < 1e-7) { out[y * W + x] = -1.0f; continue; }
+                double deg = atan2(-A, -B) * (180.0 / 3.141592653589793);
+                if (deg < 0) deg += 360.0;
+                if (deg >= 360.0) deg -= 360.0;
+                out[y * W + x] = (float)deg;
+            }
+        }
+}
+
 XO_EXPORT int xo_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

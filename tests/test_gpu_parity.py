@@ -477,3 +477,53 @@ def test_crosstab_vs_reference_outputs(xb, refout):
     np.testing.assert_array_equal(np.asarray(df.values, dtype=np.float64), r["crosstab.sub.table"])
     with pytest.raises(ValueError):
         xb.zonal_crosstab(zones, values, agg="median")
+
+
+def test_geodesic_vs_reference_outputs(xb, refout):
+    r = refout
+    z = r["geodesic.dem"]
+
+    def grid(data, lat, lon, two_d=False):
+        g = xb.DataArray(data, dims=("lat", "lon"))
+        if two_d:
+            g.coords["latitude"], g.coords["longitude"] = lat, lon
+        else:
+            g["lat"], g["lon"] = lat, lon
+        return g
+
+    for data in (dev(z), dev(z.astype(np.float32))):       # float64 and float32 elevation
+        tol = dict(rtol=1e-5, atol=1e-6) if data.dtype == torch.float64 else dict(rtol=2e-3, atol=2e-3)
+        g = grid(data, r["geodesic.lat"], r["geodesic.lon"])
+        s = host(xb.slope(g, method="geodesic"))
+        assert s.dtype == np.float32
+        np.testing.assert_allclose(s, r["geodesic.slope"], equal_nan=True, **tol)
+        if data.dtype == torch.float64:
+            np.testing.assert_allclose(host(xb.slope(g, method="geodesic", z_unit="foot")), r["geodesic.slope_ft"],
+                                       equal_nan=True, **tol)
+            a = host(xb.aspect(g, method="geodesic"))
+            ref = r["geodesic.aspect"]
+            np.testing.assert_array_equal(np.isnan(a), np.isnan(ref))
+            np.testing.assert_array_equal(a == -1, ref == -1)
+            m = ~np.isnan(ref) & (ref != -1)
+            d = np.abs(a[m] - ref[m])
+            assert np.minimum(d, 360 - d).max() < 1e-3
+            g2 = grid(data, r["geodesic.lat2d"], r["geodesic.lon2d"], two_d=True)
+            np.testing.assert_allclose(host(xb.slope(g2, method="geodesic")), r["geodesic.slope_2d"], equal_nan=True,
+                                       **tol)
+            a2 = host(xb.aspect(g2, method="geodesic"))
+            ref2 = r["geodesic.aspect_2d"]
+            m = ~np.isnan(ref2) & (ref2 != -1)
+            d = np.abs(a2[m] - ref2[m])
+            assert np.minimum(d, 360 - d).max() < 1e-3
+    # numpy in -> numpy out
+    gh = grid(z, r["geodesic.lat"], r["geodesic.lon"])
+    sh = xb.slope(gh, method="geodesic").data
+    assert isinstance(sh, np.ndarray)
+    np.testing.assert_allclose(sh, r["geodesic.slope"], rtol=1e-5, atol=1e-6, equal_nan=True)
+    # larger regular grid vs the oracle
+    rng = np.random.default_rng(4)
+    zz = terrain(rng, 300, 400).astype(np.float64)
+    lat, lon = np.linspace(40.0, 39.5, 300), np.linspace(-105.0, -104.2, 400)
+    ref = o.geodesic(zz, np.broadcast_to(lat[:, None], zz.shape), np.broadcast_to(lon[None, :], zz.shape), nthreads=8)
+    got = host(xb.slope(grid(dev(zz), lat, lon), method="geodesic"))
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6, equal_nan=True)

@@ -63,8 +63,16 @@ def test_error_types_before_any_device_work():
     r = raster(np.zeros((4, 4), np.float32), attrs={"res": (1, 1)})
     with pytest.raises(ValueError):
         xb.slope(r, method="spherical")                      # slope.py:334-337
-    with pytest.raises(NotImplementedError):
-        xb.slope(r, method="geodesic")
+    with pytest.raises(ValueError):
+        xb.slope(r, method="geodesic")                       # no lat/lon coordinates (utils.py:680-684)
+    g = raster(np.zeros((4, 4), np.float32))
+    g["y"] = np.linspace(5000.0, 2000.0, 4)                  # projected metres, not degrees
+    g["x"] = np.linspace(0.0, 3.0, 4)
+    with pytest.raises(ValueError):
+        xb.slope(g, method="geodesic")
+    g["y"] = np.linspace(46.0, 45.9, 4)
+    with pytest.raises(ValueError):
+        xb.aspect(g, method="geodesic", z_unit="furlong")
     with pytest.raises(ValueError):
         xb.aspect(r, method="nope")
     with pytest.raises(RuntimeError):

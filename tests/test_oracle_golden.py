@@ -231,3 +231,21 @@ def test_crosstab_vs_reference(refout):
                      nodata_values=12.0)
     table = np.column_stack([res["zone"], res[11.0], res[13.0]]).astype(np.float64)
     np.testing.assert_array_equal(table, r["crosstab.sub.table"])
+
+
+def test_geodesic_vs_reference(refout):
+    r = refout
+    z = r["geodesic.dem"]
+    lat2 = np.broadcast_to(r["geodesic.lat"][:, None], z.shape)
+    lon2 = np.broadcast_to(r["geodesic.lon"][None, :], z.shape)
+    # libm vs Numba's sin/cos may differ in the last f64 bit -> compare the f32 outputs closely
+    np.testing.assert_allclose(o.geodesic(z, lat2, lon2), r["geodesic.slope"], rtol=1e-6, atol=1e-7, equal_nan=True)
+    np.testing.assert_allclose(o.geodesic(z, lat2, lon2, z_factor=0.3048), r["geodesic.slope_ft"], rtol=1e-6,
+                               atol=1e-7, equal_nan=True)
+    np.testing.assert_allclose(o.geodesic(z, lat2, lon2, aspect=True), r["geodesic.aspect"], rtol=1e-6, atol=1e-4,
+                               equal_nan=True)
+    np.testing.assert_allclose(o.geodesic(z, r["geodesic.lat2d"], r["geodesic.lon2d"]), r["geodesic.slope_2d"],
+                               rtol=1e-6, atol=1e-7, equal_nan=True)
+    np.testing.assert_allclose(o.geodesic(z, r["geodesic.lat2d"], r["geodesic.lon2d"], aspect=True),
+                               r["geodesic.aspect_2d"], rtol=1e-6, atol=1e-4, equal_nan=True)
+    assert (r["geodesic.aspect"] == -1).any() and np.isnan(r["geodesic.slope"][1:-1, 1:-1]).any()

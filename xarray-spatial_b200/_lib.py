@@ -38,6 +38,7 @@ def _declare(lib):
         "xrs_curvature_f32": [P, I64, P, I64, I64, I64, D, P],
         "xrs_hillshade_f32": [P, I64, P, I64, I64, I64, D, D, P],
         "xrs_surface_suite_f32": [P, I64, P, P, P, P, I64, I64, I64, D, D, D, D, P],
+        "xrs_geodesic": [P, I, I64, P, P, I, P, I64, I64, I64, D, I, P],
         "xrs_focal_mean_f32": [P, I64, P, I64, I64, I64, P, I, P],
         "xrs_focal_mean_f64": [P, I64, P, I64, I64, I64, P, I, P],
         "xrs_focal_mean_f32_f64": [P, I64, P, I64, I64, I64, P, I, P],

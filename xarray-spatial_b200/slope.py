@@ -1,8 +1,8 @@
 """xrspatial.slope on the B200 backend (reference: slope.py:271-371, planar Horn method)."""
 from ._xr import DataArray
 from .dataset_support import supports_dataset
-from .utils import (ArrayTypeFunctionMapping, get_dataarray_resolution, run_stencil_device,
-                    run_stencil_host)
+from .utils import (Z_UNITS, ArrayTypeFunctionMapping, extract_latlon, get_dataarray_resolution,
+                    run_geodesic, run_stencil_device, run_stencil_host)
 
 
 def _run_numpy(data, cellsize_x, cellsize_y):
@@ -18,12 +18,16 @@ def _run_cupy(data, cellsize_x, cellsize_y):
 @supports_dataset
 def slope(agg, name='slope', method='planar', z_unit='meter'):
     """Slope of `agg` in degrees (float32, 1-cell NaN ring).  Same signature and metadata
-    contract as the reference; ``method='geodesic'`` is outside this backend's scope."""
+    contract as the reference; ``method='geodesic'`` fits a plane in the local ECEF tangent frame
+    (geodesic.py) and needs lat/lon coordinates on the DataArray."""
     if method not in ('planar', 'geodesic'):
         raise ValueError(f"method must be 'planar' or 'geodesic', got {method!r}")
     if method == 'geodesic':
-        raise NotImplementedError("method='geodesic' is not part of the B200 stencil hot path "
-                                  "(SURVEY.md section 8f); use the reference for it")
+        if z_unit not in Z_UNITS:
+            raise ValueError(f"z_unit must be one of {sorted(set(Z_UNITS.values()), key=str)}, got {z_unit!r}")
+        lat, lon, is_2d = extract_latlon(agg)
+        out = run_geodesic(agg.data, lat, lon, is_2d, Z_UNITS[z_unit], want_aspect=False)
+        return DataArray(out, name=name, coords=agg.coords, dims=agg.dims, attrs=agg.attrs)
     cellsize_x, cellsize_y = get_dataarray_resolution(agg)
     mapper = ArrayTypeFunctionMapping(numpy_func=_run_numpy, cupy_func=_run_cupy)
     out = mapper(agg)(agg.data, cellsize_x, cellsize_y)

@@ -206,3 +206,94 @@ def run_stencil_host(op, data, p=(), aux=(), out_dtype=np.float32, in_dtype=np.f
               ctypes.c_void_p(out.ctypes.data), H, W, _dbl_array(p), _dbl_array(aux), len(aux),
               host_device_index())
     return out
+
+
+# ----------------------------------------------------------------------------- geodesic helpers
+# z-unit factors and lat/lon extraction for method='geodesic' (utils.py:593-713)
+Z_UNITS = {
+    'meter': 1.0, 'meters': 1.0, 'm': 1.0,
+    'foot': 0.3048, 'feet': 0.3048, 'ft': 0.3048,
+    'kilometer': 1000.0, 'kilometers': 1000.0, 'km': 1000.0,
+    'mile': 1609.344, 'miles': 1609.344, 'mi': 1609.344,
+}
+_LAT_NAMES = {'lat', 'latitude', 'y'}
+_LON_NAMES = {'lon', 'longitude', 'x'}
+
+
+def _coord_values(agg, name):
+    c = agg.coords[name]
+    return np.asarray(getattr(c, "values", c))
+
+
+def _find_coord(agg, dim_name, known_names, label):
+    """A numeric coordinate named like the dimension, else any coordinate with a known name."""
+    if dim_name in agg.coords and np.issubdtype(_coord_values(agg, dim_name).dtype, np.number):
+        return _coord_values(agg, dim_name)
+    for name in agg.coords:
+        if str(name).lower() in known_names and np.issubdtype(_coord_values(agg, name).dtype, np.number):
+            return _coord_values(agg, name)
+    raise ValueError(
+        f"geodesic method requires {label} coordinates on the DataArray. "
+        f"No numeric coordinate found for dim '{dim_name}' or any of {sorted(known_names)}.")
+
+
+def _validate_geographic_range(lat, lon):
+    lat_min, lat_max = np.nanmin(lat), np.nanmax(lat)
+    lon_min, lon_max = np.nanmin(lon), np.nanmax(lon)
+    if lat_min < -90 or lat_max > 90:
+        raise ValueError(f"Latitude values must be in [-90, 90], got [{lat_min}, {lat_max}]. "
+                         f"Are your coordinates in a projected CRS?")
+    if lon_min < -180 or lon_max > 360:
+        raise ValueError(f"Longitude values must be in [-180, 360], got [{lon_min}, {lon_max}]. "
+                         f"Are your coordinates in a projected CRS?")
+    if lat_max - lat_min > 180 or lon_max - lon_min > 360:
+        raise ValueError(f"Coordinate span too large for geographic coordinates "
+                         f"(lat span={lat_max - lat_min}, lon span={lon_max - lon_min}). "
+                         f"Are your coordinates in a projected CRS?")
+
+
+def extract_latlon(agg):
+    """(lat, lon, is_2d): float64 latitude / longitude of the raster's cells -- 1-D per-row /
+    per-column vectors for a regular grid, (H, W) arrays for a curvilinear one (utils.py:608-662,
+    without materialising the broadcast for regular grids)."""
+    if agg.ndim < 2:
+        raise ValueError(f"geodesic method requires a 2-D DataArray, got {agg.ndim}-D")
+    dim_y, dim_x = agg.dims[-2], agg.dims[-1]
+    lat = np.asarray(_find_coord(agg, dim_y, _LAT_NAMES, 'latitude'), dtype=np.float64)
+    lon = np.asarray(_find_coord(agg, dim_x, _LON_NAMES, 'longitude'), dtype=np.float64)
+    if lat.ndim == 1 and lon.ndim == 1:
+        is_2d = False
+    elif lat.ndim == 2 and lon.ndim == 2:
+        is_2d = True
+    else:
+        raise ValueError(f"lat/lon coordinates must be both 1-D or both 2-D, got lat={lat.ndim}-D and lon={lon.ndim}-D")
+    _validate_geographic_range(lat, lon)
+    return np.ascontiguousarray(lat), np.ascontiguousarray(lon), is_2d
+
+
+def run_geodesic(data, lat, lon, is_2d, z_factor, want_aspect):
+    """xrs_geodesic on a device or host raster; result in the container type of `data`."""
+    host_in = isinstance(data, np.ndarray)
+    if host_in:
+        t = torch.from_numpy(np.ascontiguousarray(data)).cuda()
+    else:
+        t = as_device_tensor(data)
+    if t.dim() != 2:
+        raise ValueError("expected a 2-D raster, got %d-D" % t.dim())
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float64)           # the reference computes on data.astype(float64), slope.py:169
+    if t.numel() and t.stride(1) != 1:
+        t = t.contiguous()
+    H, W = t.shape
+    out = torch.empty((H, W), dtype=torch.float32, device=t.device)
+    if H and W:
+        lat_t = torch.as_tensor(lat, dtype=torch.float64, device=t.device).contiguous()
+        lon_t = torch.as_tensor(lon, dtype=torch.float64, device=t.device).contiguous()
+        with torch.cuda.device(t.device):
+            _lib.call("xrs_geodesic", ctypes.c_void_p(t.data_ptr()), 0 if t.dtype == torch.float32 else 1,
+                      t.stride(0) * t.element_size(), ctypes.c_void_p(lat_t.data_ptr()),
+                      ctypes.c_void_p(lon_t.data_ptr()), 1 if is_2d else 0, ctypes.c_void_p(out.data_ptr()),
+                      out.stride(0) * 4, H, W, float(z_factor), 1 if want_aspect else 0, stream_ptr(t))
+    if host_in:
+        return out.cpu().numpy()
+    return like_container(out, data)
