@@ -527,3 +527,42 @@ def test_geodesic_vs_reference_outputs(xb, refout):
     ref = o.geodesic(zz, np.broadcast_to(lat[:, None], zz.shape), np.broadcast_to(lon[None, :], zz.shape), nthreads=8)
     got = host(xb.slope(grid(dev(zz), lat, lon), method="geodesic"))
     np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6, equal_nan=True)
+
+
+def test_pitched_and_ragged_inputs(xb):
+    """Row pitch > W (a column slice of a wider raster), widths that are not a multiple of 4 or of
+    the 128-cell strip, and a misaligned base pointer all give the oracle's values."""
+    rng = np.random.default_rng(17)
+    big = terrain(rng, 260, 1100, nans=0.003)
+    t = dev(big)
+    for (x0, x1) in ((0, 1024), (4, 1028), (8, 524), (0, 1099), (3, 770), (128, 131)):
+        view = t[:, x0:x1]                       # pitch 1100 * 4 bytes, not contiguous
+        ref_in = big[:, x0:x1]
+        got = host(xb.slope(da(xb, view)))
+        assert_close_f32(got, o.slope(ref_in, 30.0, 30.0, nthreads=8), what="slope view %d:%d" % (x0, x1))
+        assert_close_f32(host(xb.mean(da(xb, view))), o.focal_mean(ref_in, nthreads=8), atol=0,
+                         what="mean view %d:%d" % (x0, x1))
+    # W = 1100 (multiple of 4, not of 128): TMA path with a ragged last strip
+    assert_close_f32(host(xb.hillshade(da(xb, t))), o.hillshade(big, nthreads=8), what="hillshade 1100")
+    assert used_tma(xb) == 1
+    # negative cell size in y (descending coordinates, utils.py:204-230): slope squares it
+    agg = xb.DataArray(t, dims=("y", "x"))
+    agg["y"] = np.linspace(260 * 30.0, 30.0, 260)
+    agg["x"] = np.linspace(0.0, 1099 * 30.0, 1100)
+    assert_close_f32(host(xb.slope(agg)), o.slope(big, 30.0, -30.0, nthreads=8), what="negative cellsize_y")
+
+
+def test_integer_and_f64_inputs_are_cast_like_the_reference(xb):
+    # tests/test_slope.py:70-79 parametrises over int32/int64/uint32/uint64/float32/float64
+    base = np.random.default_rng(2841).integers(-100, 100, size=(10, 15))
+    ref = o.slope(base.astype(np.float32), 1, 1)
+    for dt in (np.int32, np.int64, np.float32, np.float64):
+        got = host(xb.slope(da(xb, dev(base.astype(dt)), res=(1, 1))))
+        assert got.dtype == np.float32
+        assert_close_f32(got, ref, what=str(dt))
+        goth = xb.slope(da(xb, base.astype(dt), res=(1, 1))).data
+        assert_close_f32(goth, ref, what="host " + str(dt))
+    for dt in (np.uint8, np.uint16):
+        got = host(xb.ndvi(da(xb, dev(np.array([[1, 1], [1, 1]], dtype=dt))),
+                           da(xb, dev(np.array([[0, 2], [1, 2]], dtype=dt)))))
+        np.testing.assert_allclose(got, [[1, -0.33333334], [0, -0.33333334]], rtol=1e-6)
