@@ -53,6 +53,13 @@ def add(name, ms, bytes_per_cell, ncells=cells, note=""):
 
 
 add("slope", timeit(lambda: xb.slope(agg)), 8)
+odd = xb.DataArray(dem[:, :side - 2], dims=("y", "x"), attrs={"res": (30.0, 30.0)})   # W % 4 != 0 -> direct-load kernel
+add("slope, direct-load path (W-2)", timeit(lambda: xb.slope(odd)), 8, ncells=side * (side - 2))
+from xrspatial_b200.slope import slope as _sl
+lat = np.linspace(46.5, 40.0, side); lon = np.linspace(7.0, 13.5, side)
+geo = xb.DataArray(dem[: side // 4], dims=("lat", "lon")); geo["lat"] = lat[: side // 4]; geo["lon"] = lon
+add("slope geodesic (f32 elev, regular grid)", timeit(lambda: _sl(geo, method="geodesic"), n=3), 8, ncells=dem[: side // 4].numel(),
+    note="FP64-bound: ~300 FP64 ops per cell")
 add("aspect", timeit(lambda: xb.aspect(agg)), 8)
 add("curvature", timeit(lambda: xb.curvature(agg)), 8)
 add("hillshade", timeit(lambda: xb.hillshade(agg)), 8)

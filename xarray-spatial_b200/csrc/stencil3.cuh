@@ -17,9 +17,10 @@
 //     registers and combine them with the new row ("push, then emit the row above");
 //   * left / right neighbours come from warp shuffles (strip-edge lanes read the pad);
 //   * outputs are written as float4 with streaming stores.
-// A second loader (`DirectSrc`) reads global memory with bounds checks for rasters TMA
-// cannot describe (width not a multiple of 4 cells, unaligned pitch); it drives the very
-// same operator code.
+// Rasters TMA cannot describe (width not a multiple of 4 cells, unaligned base / pitch) run the
+// same pipeline with cp.async fills (stencil3_cpasync_kernel); a plain bounds-checked
+// direct-load kernel is kept as the reference implementation of the loader.  All three drive
+// the very same operator code.
 #pragma once
 #include "common.cuh"
 
@@ -62,19 +63,18 @@ template <typename T> __device__ __forceinline__ Row6<T> load_row_smem(const T *
     return o;
 }
 
+// Direct global loads with bounds checks (out-of-raster cells read as NaN): six independent scalar
+// loads per lane and row, so that several rows can be in flight at once.
 template <typename T>
 __device__ __forceinline__ Row6<T> load_row_direct(const T *in, int64_t pitch_elems, int64_t H,
-                                                   int64_t W, int64_t y, int64_t x0, int lane) {
+                                                   int64_t W, int64_t y, int64_t x) {
     Row6<T> o;
     const bool yin = (y >= 0) && (y < H);
     const T *rp = in + (yin ? y : 0) * pitch_elems;
-    const int64_t x = x0 + kLaneCells * lane;
+    o.l = (yin && x >= 1 && x - 1 < W) ? __ldg(rp + x - 1) : nan_of<T>();
 #pragma unroll
     for (int i = 0; i < 4; ++i) o.c[i] = (yin && (x + i) < W) ? __ldg(rp + x + i) : nan_of<T>();
-    o.l = shfl_up1(o.c[3]);
-    o.r = shfl_dn1(o.c[0]);
-    if (lane == 0) o.l = (yin && x0 >= 1) ? __ldg(rp + x0 - 1) : nan_of<T>();
-    if (lane == 31) o.r = (yin && (x0 + kStripW) < W) ? __ldg(rp + x0 + kStripW) : nan_of<T>();
+    o.r = (yin && (x + 4) < W) ? __ldg(rp + x + 4) : nan_of<T>();
     return o;
 }
 
@@ -230,18 +230,124 @@ stencil3_direct_kernel(const typename Op::in_t *__restrict__ in, int64_t in_pitc
         Op op(prm);
         const int64_t xl = x0 + kLaneCells * lane;
         const int nvalid = (int)max((int64_t)0, min((int64_t)4, g.W - xl));
-        for (int64_t yin = y0 - 1; yin <= y1; ++yin) {
-            const Row6<T> row = load_row_direct<T>(in, in_pitch_elems, g.H, g.W, yin, x0, lane);
-            Vec4<TO> o[Op::kOutputs];
-            op.step(row, o);
-            const int64_t yout = yin - 1;
-            if (yout >= y0 && nvalid > 0) {
+        // batches of kBatch rows: all loads of a batch are issued before the first row is consumed
+        // (software pipelining; the operator state update itself stays branch-free)
+        constexpr int kBatch = 4;
+        for (int64_t yb = y0 - 1; yb <= y1; yb += kBatch) {
+            Row6<T> rows[kBatch];
 #pragma unroll
-                for (int k = 0; k < Op::kOutputs; ++k)
-                    if (outs.p[k] != nullptr)
-                        store4<TO>(outs.p[k] + yout * outs.pitch_elems + xl, o[k], vec_ok != 0, nvalid);
+            for (int u = 0; u < kBatch; ++u) rows[u] = load_row_direct<T>(in, in_pitch_elems, g.H, g.W, yb + u, xl);
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                Vec4<TO> o[Op::kOutputs];
+                op.step(rows[u], o);
+                const int64_t yout = yb + u - 1;
+                if (yout >= y0 && yout < y1 && nvalid > 0) {
+#pragma unroll
+                    for (int k = 0; k < Op::kOutputs; ++k)
+                        if (outs.p[k] != nullptr)
+                            store4<TO>(outs.p[k] + yout * outs.pitch_elems + xl, o[k], vec_ok != 0, nvalid);
+                }
             }
         }
+    }
+}
+
+// ----------------------------------------------------------------------------- cp.async kernel
+// Same warp-strip pipeline for rasters TMA cannot describe (width not a multiple of 4 cells, base
+// or pitch not 16-byte aligned): the per-warp ring is filled with 4-/8-byte cp.async copies
+// (coalesced: lane i copies cells i, i+32, ... of the box row; out-of-raster cells are written
+// as NaN with plain stores), completion is tracked with cp.async groups instead of mbarriers.
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <typename T> __device__ __forceinline__ void cp_async_elem(T *dst, const T *src) {
+    if constexpr (sizeof(T) == 4)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+template <typename Op, int ROWS, int STAGES>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+stencil3_cpasync_kernel(const typename Op::in_t *__restrict__ in, int64_t in_pitch_elems,
+                        const __grid_constant__ typename Op::Params prm, const OutPtrs<Op> outs,
+                        const StripGeom g, int vec_ok) {
+    using T = typename Op::in_t;
+    using TO = typename Op::out_t;
+    constexpr int kStageElems = ROWS * kBoxW;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T *ring = reinterpret_cast<T *>(smem_raw) + (size_t)warp * STAGES * kStageElems;
+
+    const int64_t n_tasks = (int64_t)g.n_strips * g.n_segs;
+    const int64_t total_warps = (int64_t)gridDim.x * kWarpsPerCta;
+    for (int64_t task = (int64_t)blockIdx.x * kWarpsPerCta + warp; task < n_tasks; task += total_warps) {
+        const int seg = (int)(task / g.n_strips), strip = (int)(task % g.n_strips);
+        const int64_t x0 = (int64_t)strip * kStripW;
+        const int64_t y0 = (int64_t)seg * g.seg_rows;
+        const int64_t y1 = min(y0 + (int64_t)g.seg_rows, g.H);
+        const int rows_in = (int)(y1 - y0) + 2;
+        const int n_chunks = (rows_in + ROWS - 1) / ROWS;
+        const int64_t bx = x0 - kPad, by = y0 - 1;
+
+        auto fill = [&](int c) {  // chunk c -> stage c % STAGES
+            if (c < n_chunks) {
+                T *dst = ring + (c % STAGES) * kStageElems;
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    const int64_t y = by + (int64_t)c * ROWS + r;
+                    const bool yin = (y >= 0) && (y < g.H);
+                    const T *rp = in + (yin ? y : 0) * in_pitch_elems;
+#pragma unroll
+                    for (int j0 = 0; j0 < kBoxW; j0 += 32) {
+                        const int j = j0 + lane;
+                        const int64_t x = bx + j;
+                        if (j < kBoxW) {
+                            if (yin && x >= 0 && x < g.W) cp_async_elem<T>(dst + r * kBoxW + j, rp + x);
+                            else dst[r * kBoxW + j] = nan_of<T>();
+                        }
+                    }
+                }
+            }
+            cp_async_commit();  // one group per chunk slot, possibly empty
+        };
+
+#pragma unroll
+        for (int c = 0; c < STAGES - 1; ++c) fill(c);
+
+        Op op(prm);
+        const int64_t xl = x0 + kLaneCells * lane;
+        const int nvalid = (int)max((int64_t)0, min((int64_t)4, g.W - xl));
+        const int seg_h = (int)(y1 - y0);
+        const T *lane_smem = ring + kPad + kLaneCells * lane;
+        TO *optr[Op::kOutputs];
+#pragma unroll
+        for (int k = 0; k < Op::kOutputs; ++k) optr[k] = outs.p[k] + (y0 - 3) * outs.pitch_elems + xl;
+
+        for (int c = 0; c < n_chunks; ++c) {
+            fill(c + STAGES - 1);
+            cp_async_wait<STAGES - 1>();  // this lane's copies of chunk c have landed ...
+            __syncwarp();                 // ... and so have the other lanes'
+            const T *buf = lane_smem + (c % STAGES) * kStageElems;
+            const int rel = c * ROWS - 2;
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const Row6<T> row = load_row_smem<T>(buf + r * kBoxW);
+                Vec4<TO> o[Op::kOutputs];
+                op.step(row, o);
+                const bool st = nvalid > 0 && (unsigned)(rel + r) < (unsigned)seg_h;
+#pragma unroll
+                for (int k = 0; k < Op::kOutputs; ++k) {
+                    optr[k] += outs.pitch_elems;
+                    if (st && (Op::kOutputs == 1 || outs.p[k] != nullptr))
+                        store4<TO>(optr[k], o[k], vec_ok != 0, nvalid);
+                }
+            }
+            __syncwarp();  // every lane is done with this stage before it is refilled
+        }
+        cp_async_wait<0>();
     }
 }
 
@@ -322,13 +428,21 @@ int launch_stencil3(const typename Op::in_t *in, int64_t in_pitch_bytes, const t
         li.smem_bytes = (int)smem;
         kern<<<(unsigned)grid, kWarpsPerCta * 32, smem, stream>>>(tmap, prm, outs, g);
     } else {
-        int64_t grid = (int64_t)sms * 4;
+        // smaller ring than the TMA path's is not needed: same geometry, cp.async fill
+        constexpr size_t smem = (size_t)kWarpsPerCta * STAGES * ROWS * kBoxW * sizeof(T);
+        auto kern = stencil3_cpasync_kernel<Op, ROWS, STAGES>;
+        XRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerCta * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 2) per_sm = 2;
+        int64_t grid = (int64_t)sms * per_sm;
         if (grid > ctas_needed) grid = ctas_needed;
         li.used_tma = 0;
         li.grid = (int)grid;
-        li.smem_bytes = 0;
-        stencil3_direct_kernel<Op><<<(unsigned)grid, kWarpsPerCta * 32, 0, stream>>>(
-            in, in_pitch_bytes / (int64_t)sizeof(T), prm, outs, g, out_vec_ok ? 1 : 0);
+        li.smem_bytes = (int)smem;
+        kern<<<(unsigned)grid, kWarpsPerCta * 32, smem, stream>>>(in, in_pitch_bytes / (int64_t)sizeof(T), prm, outs, g,
+                                                                out_vec_ok ? 1 : 0);
     }
     XRS_CUDA(cudaGetLastError());
     return XRS_OK;
