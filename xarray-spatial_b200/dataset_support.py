@@ -1,54 +1,70 @@
-"""Dataset fan-out decorators with the reference's contract (dataset_support.py:11-80)."""
+"""Dataset fan-out for DataArray operators.
+
+Behavioural contract of the reference's decorators (xrspatial/dataset_support.py:11-80):
+
+* ``supports_dataset``: a one-raster operator called with a Dataset runs once per data variable;
+  the variable's name is passed as ``name=`` when the operator takes such a parameter; the
+  results come back as a Dataset carrying the input's attrs.
+* ``supports_dataset_bands(alias=parameter, ...)``: a multi-band operator called as
+  ``op(ds, alias='variable name', ..., other=kwargs)`` looks the bands up in the Dataset;
+  a missing alias is a TypeError, an unknown variable a ValueError.
+"""
 import functools
 import inspect
 
 from ._xr import Dataset
 
 
-def supports_dataset(func):
-    """Single-input DataArray function -> also accepts a Dataset (applied per data variable;
-    `name=<var>` is injected when the function has a `name` parameter)."""
-    has_name_param = 'name' in inspect.signature(func).parameters
+class _PerVariable(object):
+    """Callable wrapper applying a single-raster operator to every variable of a Dataset."""
 
-    @functools.wraps(func)
-    def wrapper(agg, *args, **kwargs):
-        if isinstance(agg, Dataset):
-            results = {}
-            for var_name in agg.data_vars:
-                kw = dict(kwargs)
-                if has_name_param:
-                    kw['name'] = var_name
-                results[var_name] = func(agg[var_name], *args, **kw)
-            return Dataset(results, attrs=agg.attrs)
-        return func(agg, *args, **kwargs)
+    def __init__(self, op):
+        self.op = op
+        self.passes_name = 'name' in inspect.signature(op).parameters
+        functools.update_wrapper(self, op)
 
-    return wrapper
+    def _one(self, ds, var, args, kwargs):
+        extra = dict(kwargs, name=var) if self.passes_name else kwargs
+        return self.op(ds[var], *args, **extra)
+
+    def __call__(self, agg, *args, **kwargs):
+        if not isinstance(agg, Dataset):
+            return self.op(agg, *args, **kwargs)
+        return Dataset({var: self._one(agg, var, args, kwargs) for var in agg.data_vars}, attrs=agg.attrs)
 
 
-def supports_dataset_bands(**band_param_map):
-    """Multi-band function -> also accepts `f(ds, nir='B8', red='B4', ...)`."""
+def supports_dataset(op):
+    wrapper = _PerVariable(op)
 
-    def decorator(func):
-        @functools.wraps(func)
-        def wrapper(*args, **kwargs):
+    @functools.wraps(op)
+    def call(agg, *args, **kwargs):
+        return wrapper(agg, *args, **kwargs)
+
+    return call
+
+
+def _resolve_bands(ds, aliases, kwargs):
+    """Translate ``alias='variable'`` keywords into ``parameter=DataArray`` keywords."""
+    resolved = {k: v for k, v in kwargs.items() if k not in aliases}
+    for alias, parameter in aliases.items():
+        try:
+            variable = kwargs[alias]
+        except KeyError:
+            raise TypeError(f"'{alias}' keyword required when passing a Dataset") from None
+        if variable not in ds.data_vars:
+            raise ValueError(f"'{variable}' not in Dataset. Available: {list(ds.data_vars)}")
+        resolved[parameter] = ds[variable]
+    return resolved
+
+
+def supports_dataset_bands(**aliases):
+    def decorate(op):
+        @functools.wraps(op)
+        def call(*args, **kwargs):
             if args and isinstance(args[0], Dataset):
-                ds = args[0]
-                func_kwargs = {}
-                used = set()
-                for alias, param in band_param_map.items():
-                    if alias not in kwargs:
-                        raise TypeError(f"'{alias}' keyword required when passing a Dataset")
-                    var_name = kwargs[alias]
-                    if var_name not in ds.data_vars:
-                        raise ValueError(f"'{var_name}' not in Dataset. Available: {list(ds.data_vars)}")
-                    func_kwargs[param] = ds[var_name]
-                    used.add(alias)
-                for k, v in kwargs.items():
-                    if k not in used:
-                        func_kwargs[k] = v
-                return func(**func_kwargs)
-            return func(*args, **kwargs)
+                return op(**_resolve_bands(args[0], aliases, kwargs))
+            return op(*args, **kwargs)
 
-        return wrapper
+        return call
 
-    return decorator
+    return decorate
