@@ -69,74 +69,73 @@ __global__ void __launch_bounds__(256) geodesic_kernel(const __grid_constant__ G
                     ok = ok && (v == v);
                 }
             if (ok) {
-                RowTrig r3[3];
-                ColTrig c3[3];
-                double X[9], Y[9], Z[9];
-                if constexpr (!GRID2D) {
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) { r3[d] = a.rt[y + d - 1]; c3[d] = a.ct[x + d - 1]; }
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) {
-                        const RowTrig &r = r3[k / 3];
-                        const ColTrig &c = c3[k % 3];
-                        const double h = h9[k] * a.z_factor;
-                        X[k] = (r.n + h) * r.c * c.c;
-                        Y[k] = (r.n + h) * r.c * c.s;
-                        Z[k] = (kB2 / kA2 * r.n + h) * r.s;
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) {
-                        const int64_t j = (y + k / 3 - 1) * a.W + x + k % 3 - 1;
+                // centre cell first (it defines the local frame), then one neighbour at a time:
+                // ECEF -> offset -> (e, n, u) -> running sums of the normal equations.  The sums are
+                // accumulated uncentred and centred at the end (sum(de*du) = sum(e*u) - 9*me*mu);
+                // e and n are symmetric about 0 within a 3x3 window, so nothing cancels badly.
+                RowTrig rc;
+                ColTrig cc;
+                auto trig = [&](int dy, int dx, RowTrig &r, ColTrig &c) {
+                    if constexpr (!GRID2D) {
+                        r = a.rt[y + dy - 1];
+                        c = a.ct[x + dx - 1];
+                    } else {
+                        const int64_t j = (y + dy - 1) * a.W + x + dx - 1;
                         const double la = a.lat[j] * kDeg2Rad, lo = a.lon[j] * kDeg2Rad;
-                        const double sl = sin(la), cl = cos(la), so = sin(lo), co = cos(lo);
-                        const double N = kA2 / sqrt(kA2 * cl * cl + kB2 * sl * sl);
-                        const double h = h9[k] * a.z_factor;
-                        X[k] = (N + h) * cl * co;
-                        Y[k] = (N + h) * cl * so;
-                        Z[k] = (kB2 / kA2 * N + h) * sl;
-                        if (k == 4) { r3[1].s = sl; r3[1].c = cl; c3[1].s = so; c3[1].c = co; }
+                        r.s = sin(la); r.c = cos(la);
+                        r.n = kA2 / sqrt(kA2 * r.c * r.c + kB2 * r.s * r.s);
+                        c.s = sin(lo); c.c = cos(lo);
                     }
-                }
-                const double sin_lat = r3[1].s, cos_lat = r3[1].c, sin_lon = c3[1].s, cos_lon = c3[1].c;
-                const double ex = -sin_lon, ey = cos_lon;
-                const double nx = -sin_lat * cos_lon, ny = -sin_lat * sin_lon, nz = cos_lat;
-                const double ux = cos_lat * cos_lon, uy = cos_lat * sin_lon, uz = sin_lat;
-                double e9[9], n9[9], u9[9];
-                double me = 0.0, mn = 0.0, mu = 0.0;
+                };
+                auto ecef = [&](const RowTrig &r, const ColTrig &c, double h, double &X, double &Y, double &Z) {
+                    const double t = (r.n + h) * r.c;
+                    X = t * c.c;
+                    Y = t * c.s;
+                    Z = (kB2 / kA2 * r.n + h) * r.s;
+                };
+                trig(1, 1, rc, cc);
+                double Xc, Yc, Zc;
+                ecef(rc, cc, h9[4] * a.z_factor, Xc, Yc, Zc);
+                const double ex = -cc.s, ey = cc.c;
+                const double nx = -rc.s * cc.c, ny = -rc.s * cc.s, nz = rc.c;
+                const double ux = rc.c * cc.c, uy = rc.c * cc.s, uz = rc.s;
+                double Se = 0.0, Sn = 0.0, Su = 0.0, See = 0.0, Snn = 0.0, Sen = 0.0, Seu = 0.0, Snu = 0.0;
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {
-                    const double dx = X[k] - X[4], dy = Y[k] - Y[4], dz = Z[k] - Z[4];
+                    if (k == 4) continue;  // the centre contributes e = n = u = 0
+                    RowTrig r;
+                    ColTrig c;
+                    trig(k / 3, k % 3, r, c);
+                    double Xk, Yk, Zk;
+                    ecef(r, c, h9[k] * a.z_factor, Xk, Yk, Zk);
+                    const double dx = Xk - Xc, dy = Yk - Yc, dz = Zk - Zc;
                     const double ek = dx * ex + dy * ey;  // ez = 0
                     const double nk = dx * nx + dy * ny + dz * nz;
                     double uk = dx * ux + dy * uy + dz * uz;
                     uk += (ek * ek + nk * nk) * kInv2R;
-                    e9[k] = ek; n9[k] = nk; u9[k] = uk;
-                    me += ek; mn += nk; mu += uk;
+                    Se += ek; Sn += nk; Su += uk;
+                    See = fma(ek, ek, See); Snn = fma(nk, nk, Snn); Sen = fma(ek, nk, Sen);
+                    Seu = fma(ek, uk, Seu); Snu = fma(nk, uk, Snu);
                 }
-                me *= (1.0 / 9.0); mn *= (1.0 / 9.0); mu *= (1.0 / 9.0);
-                double See = 0.0, Snn = 0.0, Sen = 0.0, Seu = 0.0, Snu = 0.0;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    const double de = e9[k] - me, dn = n9[k] - mn, du = u9[k] - mu;
-                    See += de * de; Snn += dn * dn; Sen += de * dn; Seu += de * du; Snu += dn * du;
-                }
+                const double me = Se * (1.0 / 9.0), mn = Sn * (1.0 / 9.0), mu = Su * (1.0 / 9.0);
+                See -= 9.0 * me * me; Snn -= 9.0 * mn * mn; Sen -= 9.0 * me * mn;
+                Seu -= 9.0 * me * mu; Snu -= 9.0 * mn * mu;
                 const double det = See * Snn - Sen * Sen;
                 double A = 0.0, B = 0.0;
                 if (!(fabs(det) < 1e-30)) {
-                    A = (Seu * Snn - Snu * Sen) / det;
-                    B = (Snu * See - Seu * Sen) / det;
+                    const double inv = 1.0 / det;
+                    A = (Seu * Snn - Snu * Sen) * inv;
+                    B = (Snu * See - Seu * Sen) * inv;
                 }
-                const double mag = sqrt(A * A + B * B);
+                // A, B are float64; the result is float32, so the transcendental tail runs in
+                // float32 (one MUFU + a degree-7 polynomial, 2.5e-7 relative) like the planar path
+                const double m2 = A * A + B * B;
                 if (!a.want_aspect) {
-                    res = (float)(atan(mag) * kRad2Deg);
-                } else if (mag < 1e-7) {
+                    res = atan_sqrt_deg((float)m2);
+                } else if (m2 < 1e-14) {   // |(A, B)| < 1e-7 (geodesic.py:160)
                     res = -1.0f;
                 } else {
-                    double deg = atan2(-A, -B) * kRad2Deg;
-                    if (deg < 0) deg += 360.0;
-                    if (deg >= 360.0) deg -= 360.0;
-                    res = (float)deg;
+                    res = compass_deg((float)(-A), (float)(-B));   // atan2(-A, -B) folded to [0, 360)
                 }
             }
         }
