@@ -127,6 +127,27 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def synth_sample(rows, cols):
+    """The top-left rows x cols window of the benchmark DEM (same generator, same seed as the GPU
+    arm: only the INPUT is produced on the device, nothing of the timed path runs there); a
+    host-generated stand-in when no GPU is usable."""
+    try:
+        import ctypes
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("no GPU")
+        from xrspatial_b200 import _lib
+        t = torch.empty((rows, cols), dtype=torch.float32, device="cuda")
+        _lib.call("xrs_synth_terrain_f32", ctypes.c_void_p(t.data_ptr()), cols * 4, rows, cols, 0, 0, 1235, 0.0, 4000.0,
+                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        out = t.cpu().numpy()
+        del t
+        torch.cuda.empty_cache()
+        return out, "top-left %d x %d window of the benchmark DEM (xrs_synth_terrain_f32, seed 1235)" % (rows, cols)
+    except Exception:
+        return host_sample(rows, cols), "%d x %d host-generated DEM (no GPU available for the synthetic terrain)" % (rows, cols)
+
+
 def host_sample(rows, cols, seed=1234):
     """Cheap host-side DEM for the CPU arm when no GPU generated one (same statistics)."""
     rng = np.random.default_rng(seed)
@@ -146,19 +167,21 @@ def run_reference_arm(args):
     oracle.build()
     threads = host_threads()
     rows = cols = args.cpu_sample
-    sample = host_sample(rows, cols)
+    sample, sample_desc = synth_sample(rows, cols)
     times = cpu_steps(sample, threads, args.steps, args.warmup)
     dt = float(np.mean(times))
     value = 3.0 * rows * cols / dt / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32 in / f64 Horn sums (as the reference)",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "slope+hillshade+focal.mean, CPU oracle (C restatement of the reference's "
-                               "Numba/NumPy kernels), %d x %d sample per step" % (rows, cols)},
+        "config": {"workload": "slope+hillshade+focal.mean on a float32 fBm-like DEM, res=(30,30): CPU oracle "
+                               "(C restatement of the reference's Numba/NumPy kernels, which cannot travel to "
+                               "this box), bounded sample per step",
+                   "sample": sample_desc, "arithmetic": "Horn sums in f64 as Numba promotes them"},
         "cpu_baseline": {"value": value, "unit": "Mcells/s", "cores": threads, "kind": "port",
-                         "sample": "%d x %d float32 DEM, all three operators, OpenMP rows" % (rows, cols)},
+                         "sample": sample_desc + ", all three operators, OpenMP over rows"},
         "e2e": {"value": value, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -289,12 +312,13 @@ def run_gpu_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32 (Horn sums in f64, as the reference)",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "slope+hillshade+focal.mean on a %d x %d float32 fBm-like DEM, res=(30,30)%s"
                                    % (H, W, "" if n_gpus == 1 else ", row-striped over %d GPUs with 1-row NCCL "
                                       "halo exchange per step" % n_gpus),
                        "raster": [H, W], "cells_per_step": cells_step, "parallelism": "rows/%d" % n_gpus,
+                       "arithmetic": "f32 in/out; Horn sums and focal sums in f64 like the reference's Numba kernels",
                        "l2": "inputs (%.1f GiB per GPU) are larger than L2, no flush" % (hp * W * 4 / 2 ** 30)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": 3 * args.steps,

@@ -96,7 +96,13 @@ template <typename TO> __device__ __forceinline__ void store4(TO *p, const Vec4<
 
 template <typename TO> __device__ __forceinline__ void store4v(TO *p, const Vec4<TO> &v) {
     if constexpr (sizeof(TO) == 4) {
+#ifdef XRS_STORE_PLAIN
+        *reinterpret_cast<float4 *>(p) = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
+#elif defined(XRS_STORE_CG)
+        __stcg(reinterpret_cast<float4 *>(p), make_float4(v.v[0], v.v[1], v.v[2], v.v[3]));
+#else
         __stcs(reinterpret_cast<float4 *>(p), make_float4(v.v[0], v.v[1], v.v[2], v.v[3]));
+#endif
     } else {
         __stcs(reinterpret_cast<double2 *>(p), make_double2(v.v[0], v.v[1]));
         __stcs(reinterpret_cast<double2 *>(p + 2), make_double2(v.v[2], v.v[3]));
@@ -149,6 +155,12 @@ stencil3_tma_kernel(const __grid_constant__ CUtensorMap tmap,
     const int64_t n_tasks = (int64_t)g.n_strips * g.n_segs;
     const int64_t total_warps = (int64_t)gridDim.x * kWarpsPerCta;
     uint32_t phase = 0;  // bit s = parity to wait for on stage s
+#ifdef XRS_TMA_EVICT_FIRST
+    const uint64_t l2pol = l2_policy_evict_first();
+#define XRS_TMA_LOAD(dst, bar, x, y) tma_load_2d_hint(dst, &tmap, bar, x, y, l2pol)
+#else
+#define XRS_TMA_LOAD(dst, bar, x, y) tma_load_2d(dst, &tmap, bar, x, y)
+#endif
 
     for (int64_t task = (int64_t)blockIdx.x * kWarpsPerCta + warp; task < n_tasks; task += total_warps) {
         const int seg = (int)(task / g.n_strips), strip = (int)(task % g.n_strips);
@@ -164,7 +176,7 @@ stencil3_tma_kernel(const __grid_constant__ CUtensorMap tmap,
             for (int s = 0; s < STAGES; ++s)
                 if (s < n_chunks) {
                     mbar_arrive_expect_tx(&bars[s], kStageBytes);
-                    tma_load_2d(ring + s * kStageElems, &tmap, &bars[s], bx, by + s * ROWS);
+                    XRS_TMA_LOAD(ring + s * kStageElems, &bars[s], bx, by + s * ROWS);
                 }
         }
 
@@ -203,7 +215,7 @@ stencil3_tma_kernel(const __grid_constant__ CUtensorMap tmap,
             __syncwarp();  // every lane is done reading this stage
             if (lane == 0 && c + STAGES < n_chunks) {
                 mbar_arrive_expect_tx(&bars[stage], kStageBytes);
-                tma_load_2d(ring + stage * kStageElems, &tmap, &bars[stage], bx, by + (c + STAGES) * ROWS);
+                XRS_TMA_LOAD(ring + stage * kStageElems, &bars[stage], bx, by + (c + STAGES) * ROWS);
             }
             stage = (stage + 1 == STAGES) ? 0 : stage + 1;
         }
