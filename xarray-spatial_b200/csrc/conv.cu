@@ -108,7 +108,7 @@ conv2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
                 const double vb[8] = {(double)b0.x, (double)b0.y, (double)b0.z, (double)b0.w,
                                       (double)b1.x, (double)b1.y, (double)b1.z, (double)b1.w};
                 const bool full_chunk = (kb >= g.off) && (kb + 4 <= n_taps);
-                if (full_rows && full_chunk) {
+                if (full_chunk && full_rows) {
                     const double *w0 = cw.w + (j * g.kw + kb - g.off);  // kernel row j, taps kb-off ..
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
@@ -120,6 +120,24 @@ conv2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
                             for (int c = 0; c < 4; ++c) {
                                 acc[r][c] = fma(wv, va[c + tt], acc[r][c]);
                                 acc[r][4 + c] = fma(wv, vb[c + tt], acc[r][4 + c]);
+                            }
+                        }
+                    }
+                } else if (full_chunk) {
+                    // lead-in / lead-out rows of the window: some output rows have no kernel row here
+                    const double *w0 = cw.w + (j * g.kw + kb - g.off);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        if (j - r >= 0 && j - r < g.kh) {  // warp-uniform
+                            const double *wr = w0 - r * g.kw;        // kernel row j - r
+#pragma unroll
+                            for (int tt = 0; tt < 4; ++tt) {
+                                const double wv = wr[tt];
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) {
+                                    acc[r][c] = fma(wv, va[c + tt], acc[r][c]);
+                                    acc[r][4 + c] = fma(wv, vb[c + tt], acc[r][4 + c]);
+                                }
                             }
                         }
                     }
