@@ -242,6 +242,9 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    parity = None
+    if rank == 0 and n_gpus == 1 and not args.skip_host:
+        parity = run_parity_gate(xb, stripes, attrs)     # before any timing
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
@@ -320,7 +323,7 @@ def run_gpu_arm(args):
                        "raster": [H, W], "cells_per_step": cells_step, "parallelism": "rows/%d" % n_gpus,
                        "arithmetic": "f32 in/out; Horn sums and focal sums in f64 like the reference's Numba kernels",
                        "l2": "inputs (%.1f GiB per GPU) are larger than L2, no flush" % (hp * W * 4 / 2 ** 30)},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "parity_gate": parity,
             "gpu_launches": 3 * args.steps,
         }
         print(json.dumps(line))
@@ -369,6 +372,35 @@ def run_e2e(xb, stripes, H, W, attrs, args):
             "api": "xrspatial_b200.slope/hillshade/mean on numpy DataArrays in pinned host memory "
                    "(xrs_host_stencil: chunked H2D -> kernel -> D2H pipeline); focal.mean returns float64 "
                    "like the reference's numpy path"}
+
+
+def run_parity_gate(xb, stripes, attrs, n=2048):
+    """parity gate before timing -- the three benchmark operators on the top-left
+    n x n window of the benchmark DEM against the CPU oracle (|gpu - ref| <= 1e-5 |ref| + 1e-6,
+    identical NaN masks)."""
+    import oracle
+    oracle.build()
+    n = int(min(n, stripes.h, stripes.W))
+    win = stripes.interior[:n, :n].contiguous()
+    host = win.cpu().numpy()
+    agg = xb.DataArray(win, dims=("y", "x"), attrs=attrs)
+    threads = host_threads()
+    worst = 0.0
+    for name, got, ref in (
+            ("slope", xb.slope(agg).data, oracle.slope(host, RES[0], RES[1], nthreads=threads)),
+            ("hillshade", xb.hillshade(agg).data, oracle.hillshade(host, 225, 25, nthreads=threads)),
+            ("focal.mean", xb.mean(agg).data, oracle.focal_mean(host, nthreads=threads))):
+        g = got.cpu().numpy().astype(np.float64)
+        r = np.asarray(ref, dtype=np.float64)
+        if not np.array_equal(np.isnan(g), np.isnan(r)):
+            raise AssertionError("parity gate: NaN mask of %s differs from the oracle" % name)
+        m = ~np.isnan(r)
+        e = float((np.abs(g[m] - r[m]) / (1e-5 * np.abs(r[m]) + 1e-6)).max())
+        if e > 1.0:
+            raise AssertionError("parity gate: %s is %.3g x outside the tolerance" % (name, e))
+        worst = max(worst, e)
+    return {"checked": True, "window": [n, n], "operators": ["slope", "hillshade", "focal.mean"],
+            "tolerance": "|gpu-ref| <= 1e-5*|ref| + 1e-6, NaN masks identical", "worst_err_over_tol": worst}
 
 
 def run_cpu_baseline(stripes, args):
