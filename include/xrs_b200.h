@@ -48,7 +48,7 @@ enum xrs_focal_stat {
 };
 
 /* element types for zonal inputs */
-enum xrs_dtype { XRS_F32 = 0, XRS_F64 = 1, XRS_I32 = 2, XRS_I64 = 3 };
+enum xrs_dtype { XRS_F32 = 0, XRS_F64 = 1, XRS_I32 = 2, XRS_I64 = 3, XRS_I16 = 4, XRS_U16 = 5 };
 
 int xrs_abi_version(void);
 const char *xrs_last_error_string(void);
@@ -91,6 +91,15 @@ int xrs_surface_suite_f32(const float *in, int64_t in_pitch, float *slope_out,
 int xrs_geodesic(const void *elev, int elev_dtype, int64_t elev_pitch, const double *lat,
                  const double *lon, int latlon_2d, float *out, int64_t out_pitch, int64_t H, int64_t W,
                  double z_factor, int want_aspect, xrs_stream_t s);
+
+/* Direct ingestion: slope / aspect / curvature / hillshade (op = XRS_OP_*) on a
+ * raster of int16, uint16, int32 or float64 cells (in_dtype = XRS_I16 / XRS_U16 / XRS_I32 / XRS_F64),
+ * converted to float32 in registers exactly like the reference's `.astype(np.float32)`
+ * (slope.py:58,150) but without the extra pass.  p: slope {csx, csy}; curvature {cellsize};
+ * hillshade {azimuth, altitude}.  Needs 16-byte aligned rows and W % 4 == 0, else
+ * XRS_EUNSUPPORTED (cast and use the float32 entry points). */
+int xrs_surface_typed(int op, const void *in, int in_dtype, int64_t in_pitch, float *out,
+                      int64_t out_pitch, int64_t H, int64_t W, const double *p, xrs_stream_t s);
 
 /* ------------------------------------------------------------------ focal / convolution */
 /* focal._mean_cupy (focal.py:135-146) / `_mean_numpy` (focal.py:44-67): ONE pass of the 3x3
@@ -220,6 +229,10 @@ enum xrs_op {
  *    convolve {kh, kw}; focal stat {kh, kw, stat}.  aux: excludes / kernel (host). */
 int xrs_host_stencil(int op, const void *in, void *out, int64_t H, int64_t W, const double *p,
                      const double *aux, int naux, int device);
+/* slope / aspect / curvature / hillshade on a HOST raster of int16 / uint16 / int32 / float64 cells
+ * (xrs_surface_typed behind the same pipeline; needs W % 4 == 0): the raw cells cross PCIe. */
+int xrs_host_surface_typed(int op, const void *in, int in_dtype, float *out, int64_t H, int64_t W,
+                           const double *p, int device);
 /* frees the per-device staging buffers the host path keeps between calls */
 int xrs_host_release(int device);
 /* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers that want

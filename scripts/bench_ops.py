@@ -55,6 +55,12 @@ def add(name, ms, bytes_per_cell, ncells=cells, note=""):
 add("slope", timeit(lambda: xb.slope(agg)), 8)
 odd = xb.DataArray(dem[:, :side - 2], dims=("y", "x"), attrs={"res": (30.0, 30.0)})   # W % 4 != 0 -> direct-load kernel
 add("slope, direct-load path (W-2)", timeit(lambda: xb.slope(odd)), 8, ncells=side * (side - 2))
+i16 = xb.DataArray(dem.round().to(torch.int16), dims=("y", "x"), attrs={"res": (30.0, 30.0)})
+add("slope, int16 DEM ingested directly", timeit(lambda: xb.slope(i16)), 6, note="2 B read + 4 B written per cell")
+f64 = xb.DataArray(dem[: side // 2].to(torch.float64), dims=("y", "x"), attrs={"res": (30.0, 30.0)})
+add("slope, float64 DEM ingested directly", timeit(lambda: xb.slope(f64)), 12, ncells=side * side // 2,
+    note="8 B read + 4 B written per cell")
+del i16, f64
 from xrspatial_b200.slope import slope as _sl
 lat = np.linspace(46.5, 40.0, side); lon = np.linspace(7.0, 13.5, side)
 geo = xb.DataArray(dem[: side // 4], dims=("lat", "lon")); geo["lat"] = lat[: side // 4]; geo["lon"] = lon

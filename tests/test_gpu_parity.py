@@ -566,3 +566,31 @@ def test_integer_and_f64_inputs_are_cast_like_the_reference(xb):
         got = host(xb.ndvi(da(xb, dev(np.array([[1, 1], [1, 1]], dtype=dt))),
                            da(xb, dev(np.array([[0, 2], [1, 2]], dtype=dt)))))
         np.testing.assert_allclose(got, [[1, -0.33333334], [0, -0.33333334]], rtol=1e-6)
+
+
+@pytest.mark.parametrize("dt", [np.int16, np.uint16, np.int32, np.float64])
+def test_direct_ingest_matches_cast_then_compute(xb, dt):
+    """int16 / uint16 / int32 / float64 rasters are read directly (xrs_surface_typed) and must give
+    exactly what the float32 kernels give on the `.astype(float32)` copy (slope.py:58,150)."""
+    rng = np.random.default_rng(31)
+    base = terrain(rng, 300, 512) - (1500.0 if np.issubdtype(dt, np.signedinteger) or dt == np.float64 else 0.0)
+    if dt == np.float64:
+        raw = base.astype(np.float64) * 1.000000123          # not exactly representable in f32
+    else:
+        raw = np.round(base).astype(dt)
+    f32 = raw.astype(np.float32)
+    for name, fn, kw in (("slope", xb.slope, {}), ("aspect", xb.aspect, {}), ("curvature", xb.curvature, {}),
+                         ("hillshade", xb.hillshade, dict(azimuth=300, angle_altitude=40))):
+        ref = host(fn(da(xb, dev(f32)), **kw))
+        got = fn(da(xb, dev(raw)), **kw)
+        assert used_tma(xb) == 2, "direct-ingest kernel was not selected for %s" % np.dtype(dt).name
+        assert got.data.dtype == torch.float32
+        np.testing.assert_array_equal(host(got), ref, err_msg="%s %s" % (name, np.dtype(dt).name))
+        goth = fn(da(xb, raw), **kw).data                    # host raster: raw cells cross PCIe
+        assert isinstance(goth, np.ndarray) and goth.dtype == np.float32
+        np.testing.assert_array_equal(goth, ref, err_msg="host %s %s" % (name, np.dtype(dt).name))
+    # layouts the ingest path does not take fall back to cast + float32 kernels, same values
+    odd = raw[:, :509]
+    np.testing.assert_array_equal(host(xb.slope(da(xb, dev(odd)))), host(xb.slope(da(xb, dev(odd.astype(np.float32))))))
+    np.testing.assert_array_equal(xb.slope(da(xb, np.ascontiguousarray(odd))).data,
+                                  host(xb.slope(da(xb, dev(odd.astype(np.float32))))))

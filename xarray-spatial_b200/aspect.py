@@ -1,18 +1,18 @@
 """xrspatial.aspect on the B200 backend (reference: aspect.py:274-388, planar)."""
 from ._xr import DataArray
 from .dataset_support import supports_dataset
-from .utils import (Z_UNITS, ArrayTypeFunctionMapping, extract_latlon, run_geodesic, run_stencil_device,
-                    run_stencil_host)
+from .utils import (Z_UNITS, ArrayTypeFunctionMapping, extract_latlon, run_geodesic, run_surface_device,
+                    run_surface_host)
 
 
 def _run_numpy(data):
     """replaces aspect.py:56 `_run_numpy`."""
-    return run_stencil_host("aspect", data)
+    return run_surface_host("aspect", data, ())
 
 
 def _run_cupy(data):
     """replaces aspect.py:139 `_run_cupy`; follows the CPU path (no 359.999 clamp)."""
-    return run_stencil_device("xrs_aspect_f32", data)
+    return run_surface_device("aspect", "xrs_aspect_f32", data)
 
 
 @supports_dataset

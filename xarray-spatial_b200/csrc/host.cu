@@ -50,9 +50,10 @@ static int ensure_cap(void **p, size_t *cap, size_t need) {
     return XRS_OK;
 }
 
-static int run_op(int op, const void *din, void *dout, int64_t pitch, int64_t opitch, int64_t h, int64_t W,
-                  const double *p,
-                  const double *aux, int naux, cudaStream_t s) {
+static int run_op(int op, int in_dtype, const void *din, void *dout, int64_t pitch, int64_t opitch, int64_t h,
+                  int64_t W, const double *p, const double *aux, int naux, cudaStream_t s) {
+    if (in_dtype != XRS_F32)  // raw int16 / uint16 / int32 / float64 cells: direct-ingest kernels
+        return xrs_surface_typed(op, din, in_dtype, pitch, (float *)dout, opitch, h, W, p, s);
     const float *fi = (const float *)din;
     float *fo = (float *)dout;
     switch (op) {
@@ -77,13 +78,18 @@ static int run_op(int op, const void *din, void *dout, int64_t pitch, int64_t op
 
 using namespace xrs;
 
-extern "C" int xrs_host_stencil(int op, const void *in, void *out, int64_t H, int64_t W, const double *p,
-                                const double *aux, int naux, int device) {
+static int host_pipeline(int op, int in_dtype, const void *in, void *out, int64_t H, int64_t W, const double *p,
+                         const double *aux, int naux, int device) {
     if (H <= 0 || W <= 0) return XRS_OK;
     XRS_REQUIRE(in && out, "NULL host pointer");
     XRS_REQUIRE(device >= 0 && device < 16, "device index out of range");
     XRS_REQUIRE(op >= XRS_OP_SLOPE && op <= XRS_OP_FOCAL_MEAN_F32_F64, "unknown op");
-    const int esz = (op == XRS_OP_FOCAL_MEAN_F64) ? 8 : 4;                                       // input
+    int esz = (op == XRS_OP_FOCAL_MEAN_F64) ? 8 : 4;                                             // input
+    if (in_dtype != XRS_F32) {
+        XRS_REQUIRE(op <= XRS_OP_HILLSHADE, "typed input is served for slope, aspect, curvature, hillshade");
+        XRS_REQUIRE(W % 4 == 0, "typed host input needs W % 4 == 0");
+        esz = (in_dtype == XRS_F64) ? 8 : (in_dtype == XRS_I32 ? 4 : 2);
+    }
     const int osz = (op == XRS_OP_FOCAL_MEAN_F64 || op == XRS_OP_FOCAL_MEAN_F32_F64) ? 8 : 4;  // output
     int radius = 1;
     if (op == XRS_OP_CONVOLVE || op == XRS_OP_FOCAL_STAT) {
@@ -128,7 +134,7 @@ extern "C" int xrs_host_stencil(int op, const void *in, void *out, int64_t H, in
         if (e == cudaSuccess) e = cudaEventRecord(s.in_done, c.s_in);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(c.s_k, s.in_done, 0);
         if (e != cudaSuccess) { rc = cuda_fail(e, "H2D enqueue"); break; }
-        rc = run_op(op, s.din, s.dout, pitch, opitch, h, W, p, aux, naux, c.s_k);
+        rc = run_op(op, in_dtype, s.din, s.dout, pitch, opitch, h, W, p, aux, naux, c.s_k);
         if (rc) break;
         e = cudaEventRecord(s.k_done, c.s_k);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(c.s_out, s.k_done, 0);
@@ -146,6 +152,20 @@ extern "C" int xrs_host_stencil(int op, const void *in, void *out, int64_t H, in
         rc = cuda_fail(e != cudaSuccess ? e : (e2 != cudaSuccess ? e2 : e3), "pipeline synchronize");
     cudaSetDevice(prev);
     return rc;
+}
+
+extern "C" int xrs_host_stencil(int op, const void *in, void *out, int64_t H, int64_t W, const double *p,
+                                const double *aux, int naux, int device) {
+    return host_pipeline(op, XRS_F32, in, out, H, W, p, aux, naux, device);
+}
+
+// slope / aspect / curvature / hillshade on a HOST raster of int16 / uint16 / int32 / float64 cells:
+// the raw cells travel over PCIe (half the bytes for 16-bit DEMs) and are converted on the device.
+extern "C" int xrs_host_surface_typed(int op, const void *in, int in_dtype, float *out, int64_t H, int64_t W,
+                                      const double *p, int device) {
+    XRS_REQUIRE(in_dtype == XRS_F64 || in_dtype == XRS_I32 || in_dtype == XRS_I16 || in_dtype == XRS_U16,
+                "in_dtype must be int16, uint16, int32 or float64");
+    return host_pipeline(op, in_dtype, in, out, H, W, p, nullptr, 0, device);
 }
 
 // release the per-device staging buffers (tests / interpreter shutdown)

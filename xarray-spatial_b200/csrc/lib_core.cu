@@ -75,6 +75,32 @@ bool make_tensor_map_2d(CUtensorMap *map, const void *base, int64_t pitch_bytes,
     return r == CUDA_SUCCESS;
 }
 
+// Raw-element tensor map for the direct-ingest kernels: dtype is an xrs_dtype; float64 gets the NaN
+// out-of-bounds fill, integer types are zero-filled by the hardware (the kernel patches NaN in).
+bool make_tensor_map_2d_raw(CUtensorMap *map, const void *base, int64_t pitch_bytes, int64_t H, int64_t W,
+                            int dtype, int box_w, int box_h) {
+    CUtensorMapDataType dt;
+    int esz;
+    switch (dtype) {
+        case XRS_I16: case XRS_U16: dt = CU_TENSOR_MAP_DATA_TYPE_UINT16; esz = 2; break;
+        case XRS_I32: dt = CU_TENSOR_MAP_DATA_TYPE_INT32; esz = 4; break;
+        case XRS_F64: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT64; esz = 8; break;
+        default: return false;
+    }
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || pitch_bytes % 16 != 0) return false;
+    if ((int64_t)box_w * esz % 16 != 0 || box_w > 256 || box_h > 256) return false;
+    encode_tiled_fn fn = get_encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)H};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapFloatOOBfill fill =
+        dtype == XRS_F64 ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE;
+    return fn(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, fill) == CUDA_SUCCESS;
+}
+
 }  // namespace xrs
 
 extern "C" {

@@ -1,18 +1,18 @@
 """xrspatial.curvature on the B200 backend (reference: curvature.py:111-247)."""
 from ._xr import DataArray
 from .dataset_support import supports_dataset
-from .utils import (ArrayTypeFunctionMapping, get_dataarray_resolution, run_stencil_device,
-                    run_stencil_host)
+from .utils import (ArrayTypeFunctionMapping, get_dataarray_resolution, run_surface_device,
+                    run_surface_host)
 
 
 def _run_numpy(data, cellsize):
     """replaces curvature.py:44 `_run_numpy`."""
-    return run_stencil_host("curvature", data, (cellsize,))
+    return run_surface_host("curvature", data, (cellsize,))
 
 
 def _run_cupy(data, cellsize):
     """replaces curvature.py:81 `_run_cupy`."""
-    return run_stencil_device("xrs_curvature_f32", data, cellsize)
+    return run_surface_device("curvature", "xrs_curvature_f32", data, cellsize)
 
 
 @supports_dataset

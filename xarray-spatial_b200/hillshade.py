@@ -3,19 +3,19 @@ import numpy as np
 
 from ._xr import DataArray
 from .dataset_support import supports_dataset
-from .utils import is_dask_array, is_device_array, run_stencil_device, run_stencil_host
+from .utils import is_dask_array, is_device_array, run_surface_device, run_surface_host
 
 
 def _run_numpy(data, azimuth=225, angle_altitude=25):
     """replaces hillshade.py:20 `_run_numpy`.  Returns float32 (the dtype the reference
     documents and its GPU path produces; its NumPy path yields float64 only through NumPy-2
     scalar promotion)."""
-    return run_stencil_host("hillshade", data, (azimuth, angle_altitude))
+    return run_surface_host("hillshade", data, (azimuth, angle_altitude))
 
 
 def _run_cupy(d_data, azimuth, angle_altitude):
     """replaces hillshade.py:78 `_run_cupy`."""
-    return run_stencil_device("xrs_hillshade_f32", d_data, azimuth, angle_altitude)
+    return run_surface_device("hillshade", "xrs_hillshade_f32", d_data, azimuth, angle_altitude)
 
 
 @supports_dataset

@@ -192,6 +192,47 @@ def run_stencil_device(fn_name, data, *scalars, aux=None, naux=None, extra_ints=
     return like_container(out, data)
 
 
+_INGEST_NP = {"int16": 4, "uint16": 5, "int32": 2, "float64": 1}
+
+
+def run_surface_device(op, fn_name, data, *scalars):
+    """slope / aspect / curvature / hillshade on a device raster.  int16 / uint16 / int32 / float64
+    rasters go through the direct-ingest kernels (xrs_surface_typed: no separate cast pass); other
+    dtypes are cast to float32 first, like the reference does (slope.py:150)."""
+    t = as_device_tensor(data)
+    code = _INGEST_NP.get(str(t.dtype).replace("torch.", ""))
+    if code is not None and t.dim() == 2 and t.numel() and t.stride(1) == 1:
+        H, W = t.shape
+        out = torch.empty((H, W), dtype=torch.float32, device=t.device)
+        try:
+            with torch.cuda.device(t.device):
+                _lib.call("xrs_surface_typed", _lib.OPS[op], ctypes.c_void_p(t.data_ptr()), code,
+                          t.stride(0) * t.element_size(), ctypes.c_void_p(out.data_ptr()), out.stride(0) * 4, H, W,
+                          _dbl_array(scalars), stream_ptr(t))
+            return like_container(out, data)
+        except NotImplementedError:
+            pass  # layout the ingest kernels do not take (odd width, misaligned rows): cast instead
+    return run_stencil_device(fn_name, data, *scalars)
+
+
+def run_surface_host(op, data, p=()):
+    """Same for numpy rasters: raw 16-bit / int32 / float64 cells cross PCIe and are converted on the
+    device when the layout allows it, else the raster is cast on the host (slope.py:58)."""
+    from . import _hostmem
+    code = _INGEST_NP.get(data.dtype.name)
+    if code is not None and data.ndim == 2 and data.size and data.shape[1] % 4 == 0:
+        d = np.ascontiguousarray(data)
+        H, W = d.shape
+        out = _hostmem.empty((H, W), np.float32)
+        try:
+            _lib.call("xrs_host_surface_typed", _lib.OPS[op], ctypes.c_void_p(d.ctypes.data), code,
+                      ctypes.c_void_p(out.ctypes.data), H, W, _dbl_array(p), host_device_index())
+            return out
+        except NotImplementedError:
+            pass
+    return run_stencil_host(op, data, p)
+
+
 def run_stencil_host(op, data, p=(), aux=(), out_dtype=np.float32, in_dtype=np.float32):
     """Call xrs_host_stencil on a numpy raster; the result is a numpy array in pinned memory."""
     from . import _hostmem
