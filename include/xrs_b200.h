@@ -126,6 +126,14 @@ int xrs_convolve2d_f32(const float *in, int64_t in_pitch, float *out, int64_t ou
 int xrs_focal_stat_f32(const float *in, int64_t in_pitch, float *out, int64_t out_pitch,
                        int64_t H, int64_t W, const double *kernel, int kh, int kw, int stat,
                        xrs_stream_t s);
+/* focal.focal_stats (focal.py:800-878: seven `apply` calls stacked by xr.concat) in one pass:
+ * plane i of `out` (planes `plane_stride` bytes apart, rows `out_pitch` bytes apart) receives
+ * statistic stats[i] (xrs_focal_stat ids, no duplicates, n_stats <= 7).  The tile is loaded
+ * once and swept twice for all seven statistics; results are bit-identical to n_stats calls
+ * of xrs_focal_stat_f32. */
+int xrs_focal_stats_multi_f32(const float *in, int64_t in_pitch, float *out, int64_t out_pitch,
+                              int64_t plane_stride, int64_t H, int64_t W, const double *kernel,
+                              int kh, int kw, const int *stats, int n_stats, xrs_stream_t s);
 
 /* focal.hotspots (focal.py:1050-1125) = convolve_2d with kernel / kernel.sum(), then
  * z = (mean - global_mean) / global_std classified into {0, +-90, +-95, +-99} (int8).
@@ -240,8 +248,9 @@ int xrs_host_release(int device);
 int xrs_host_alloc(void **ptr, int64_t bytes);
 int xrs_host_free(void *ptr);
 
-/* test / profiling hooks: did the last stencil launch on this thread use the TMA kernel,
- * and with how many CTAs */
+/* test / profiling hooks: which kernel the last launch on this thread chose -- 0 cp.async strip
+ * kernel, 1 TMA strip kernel, 2 direct-ingest TMA kernel, 3 summed-area box convolve, 4 generic
+ * tiled convolve, 5 bounds-checked convolve fallback, 6 fused focal statistics -- and with how many CTAs */
 int xrs_debug_last_used_tma(void);
 int xrs_debug_last_grid(void);
 

@@ -78,13 +78,20 @@ add("focal.mean f64", timeit(lambda: xb.mean(a64)), 16, ncells=d64.numel())
 del d64, a64
 for k in (3, 9, 25):
     kern = np.ones((k, k)) / (k * k)
-    sub = dem if k == 3 else dem[: side // (2 if k == 9 else 8)]
-    add("convolve_2d k=%d" % k, timeit(lambda: convolve_2d(sub, kern), n=max(3, reps // 2)), 8, ncells=sub.numel(),
-        note="f64 accumulate; bound = FP64 FMA rate for k>=5")
+    add("convolve_2d k=%d uniform (ones/k^2)" % k, timeit(lambda: convolve_2d(dem, kern), n=max(3, reps // 2)), 8,
+        note="k=3: strip kernel; k>3: summed-area box path, HBM / shared-memory bound")
+krng = np.random.default_rng(7)
+for k in (9, 25):
+    kern = krng.standard_normal((k, k))
+    sub = dem[: side // (2 if k == 9 else 8)]
+    add("convolve_2d k=%d mixed weights" % k, timeit(lambda: convolve_2d(sub, kern), n=max(3, reps // 2)), 8,
+        ncells=sub.numel(), note="f64 accumulate; bound = FP64 FMA rate (2*k*k flop/cell)")
 k5 = np.ones((5, 5))
 sub = dem[: side // 4]
 sagg = xb.DataArray(sub, dims=("y", "x"))
-add("focal_stats mean 5x5", timeit(lambda: focal.apply(sagg, k5), n=3), 8, ncells=sub.numel())
+add("focal.apply mean 5x5", timeit(lambda: focal.apply(sagg, k5), n=3), 8, ncells=sub.numel())
+add("focal_stats 7 statistics 5x5 (fused)", timeit(lambda: focal.focal_stats(sagg, k5), n=3), 32, ncells=sub.numel(),
+    note="one pass: tile loaded once, swept twice, 7 planes written in place")
 nir, red, blue = synth(2001, 0.02, 0.6), synth(2002, 0.02, 0.6), synth(2003, 0.02, 0.6)
 A = lambda t: xb.DataArray(t, dims=("y", "x"))  # noqa: E731
 add("ndvi", timeit(lambda: xb.ndvi(A(nir), A(red))), 12)

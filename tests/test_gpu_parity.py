@@ -221,6 +221,51 @@ def test_convolve_sizes_vs_oracle(xb, k):
         assert_close_f32(got, ref, atol=1e-6 * np.nanmax(np.abs(ref[np.isfinite(ref)])), what="conv k=%d" % k)
 
 
+@pytest.mark.parametrize("kh,kw", [(5, 5), (9, 9), (25, 25), (3, 7), (7, 3), (1, 5), (25, 3)])
+def test_convolve_uniform_kernels_take_the_box_path(xb, kh, kw):
+    """All-equal taps (np.ones / k**2, the mean filter) go through the summed-area kernel; NaN / inf
+    cells poison the table and must come back through the tap-by-tap recompute."""
+    from xrspatial_b200.convolution import convolve_2d
+    rng = np.random.default_rng(100 * kh + kw)
+    z = terrain(rng, 150, 388)
+    dirty = z.copy()
+    dirty[20, 30] = np.nan
+    dirty[70, 200] = np.inf
+    dirty[100, 300] = -np.inf
+    dirty[149, 387] = np.nan
+    for w in (1.0 / (kh * kw), -0.37, 0.0):
+        kern = np.full((kh, kw), w)
+        for data in (z, dirty, (z + 1e6).astype(np.float32)):
+            ref = o.convolve_2d(data, kern, nthreads=8)
+            got = convolve_2d(dev(data), kern).cpu().numpy()
+            assert used_tma(xb) == 3
+            fin = np.isfinite(ref)
+            scale = np.abs(ref[fin]).max() if fin.any() else 1.0
+            assert_close_f32(got, ref, atol=1e-6 * max(scale, 1e-30), what="box %dx%d w=%g" % (kh, kw, w))
+    # one tap off by an ulp: generic tiled kernel
+    kern = np.full((kh, kw), 0.25)
+    kern[0, 0] = np.nextafter(0.25, 1.0)
+    if (kh, kw) != (3, 3):
+        convolve_2d(dev(z), kern)
+        assert used_tma(xb) == 4
+
+
+def test_convolve_box_path_small_and_ragged_rasters(xb):
+    from xrspatial_b200.convolution import convolve_2d
+    rng = np.random.default_rng(77)
+    kern = np.ones((9, 9)) / 81.0
+    for h, w in ((5, 8), (9, 12), (33, 128), (64, 132), (70, 260)):
+        z = terrain(rng, h, w)
+        ref = o.convolve_2d(z, kern, nthreads=4)
+        got = convolve_2d(dev(z), kern).cpu().numpy()
+        assert used_tma(xb) == 3
+        assert_close_f32(got, ref, atol=1e-6 * 4000.0, what="box 9x9 on %dx%d" % (h, w))
+    z = terrain(rng, 40, 131)            # W % 4 != 0: bounds-checked fallback
+    got = convolve_2d(dev(z), kern).cpu().numpy()
+    assert used_tma(xb) == 5
+    assert_close_f32(got, o.convolve_2d(z, kern, nthreads=4), atol=1e-6 * 4000.0, what="box 9x9 ragged")
+
+
 def test_focal_stats_tma_vs_oracle(xb):
     from xrspatial_b200 import focal
     from xrspatial_b200.convolution import circle_kernel
@@ -228,10 +273,34 @@ def test_focal_stats_tma_vs_oracle(xb):
     z = terrain(rng, 130, 256, nans=0.03)
     kern = circle_kernel(1, 1, 3)
     res = host(focal.focal_stats(da(xb, dev(z)), kern, stats_funcs=STATS))
+    assert used_tma(xb) == 6          # all seven statistics from the fused one-pass kernel
     for i, s in enumerate(STATS):
         ref = o.focal_apply(z, kern, s, nthreads=8)
         atol = 1e-6 * np.nanmax(np.abs(ref)) if s == "var" else 1e-6
         assert_close_f32(res[i], ref, atol=atol, what=s)
+
+
+@pytest.mark.parametrize("stats", [["mean", "max", "min", "range", "std", "var", "sum"], ["sum", "std"],
+                                   ["range", "mean"], ["var", "min", "max"]])
+def test_focal_stats_fused_equals_per_statistic_apply(xb, stats):
+    """The fused kernel must give, plane by plane, exactly what one `apply` per statistic gives."""
+    from xrspatial_b200 import focal
+    from xrspatial_b200.convolution import annulus_kernel, circle_kernel
+    rng = np.random.default_rng(11)
+    z = terrain(rng, 150, 388, nans=0.05)
+    z[40:60, 100:140] = np.nan          # a window-sized hole: all-NaN windows
+    agg = da(xb, dev(z))
+    for kern in (circle_kernel(1, 1, 2), annulus_kernel(1, 1, 3, 1), np.ones((3, 5))):
+        fused = focal.focal_stats(agg, kern, stats_funcs=stats)
+        assert used_tma(xb) == 6
+        assert fused.dims == ("stats", "y", "x") and list(fused.coords["stats"]) == stats
+        got = host(fused)
+        for i, s in enumerate(stats):
+            one = host(focal.apply(agg, kern, func=s))
+            np.testing.assert_array_equal(got[i], one, err_msg="%s plane differs from apply" % s)
+            ref = o.focal_apply(z, kern, s, nthreads=8)
+            atol = 1e-6 * np.nanmax(np.abs(ref)) if s == "var" else 1e-6
+            assert_close_f32(got[i], ref, atol=atol, what=s)
 
 
 def test_input_not_modified_and_metadata(xb):

@@ -45,6 +45,7 @@ def _declare(lib):
         "xrs_focal_mean_f32_f64": [P, I64, P, I64, I64, I64, P, I, P],
         "xrs_convolve2d_f32": [P, I64, P, I64, I64, I64, P, I, I, P],
         "xrs_focal_stat_f32": [P, I64, P, I64, I64, I64, P, I, I, I, P],
+        "xrs_focal_stats_multi_f32": [P, I64, P, I64, I64, I64, I64, P, I, I, P, I, P],
         "xrs_global_stats_f32": [P, I64, D, P, P],
         "xrs_hotspots_classify_f32": [P, I64, D, D, P, P],
         "xrs_normalized_ratio_f32": [P, P, P, I64, P],

@@ -14,6 +14,13 @@ namespace xrs {
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
 
+struct LaunchInfo {  // for tests / profiling: what the last launch on this thread chose
+    int used_tma;    // 0 cp.async strip kernel, 1 TMA strip kernel, 2 direct-ingest, 3 summed-area box convolve,
+                     // 4 generic tiled convolve, 5 bounds-checked fallback
+    int grid, block, smem_bytes;
+};
+LaunchInfo &last_launch_info();
+
 #define XRS_CUDA(call)                                              \
     do {                                                            \
         cudaError_t _e = (call);                                    \

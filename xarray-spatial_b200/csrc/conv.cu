@@ -11,6 +11,8 @@
 // 4 x 4 block of outputs and accumulates in float64 with FMA (the reference accumulates
 // `kernel(f64) * data(f32)` in a float64 `num`); weights are read from the kernel-parameter
 // constant bank.  Bound: FP64 FMA rate for k >= 5 (2*k*k flop/cell), HBM for k = 3.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace xrs {
@@ -181,6 +183,182 @@ conv2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
     }
 }
 
+// ----------------------------------------------------------------------------- box convolve
+// convolve_2d with a kernel whose taps are all the same weight w (np.ones((k, k)) / k**2, the
+// mean filter of the reference's docs and benchmarks): out = w * (sum of the k x k window).  The
+// window sums come from a per-tile summed-area table in float64 -- 2 adds per loaded cell and
+// 3 per output instead of k*k FMAs -- which moves the kernel from the FP64 pipe to shared-memory
+// / HBM bandwidth for every k.
+//   pass 1  column prefix sums, widening f32 -> f64 (thread per column; out-of-raster cells,
+//           which TMA delivers as NaN, count as 0: the NaN ring is set from coordinates)
+//   pass 2  row prefix sums of those (warp per row, 5 cells per lane + warp scan) -> table S
+//   pass 3  out = w * (S[bot][right] - S[bot][left] - S[top][right] + S[top][left])
+// A NaN / inf cell poisons every table entry below and to the right of it, so a non-finite
+// result is recomputed tap by tap from global memory in the generic kernel's order; finite
+// results differ from the reference's tap-order sum by f64 rounding only (~1e-13 relative to
+// the window's magnitude, against the 1e-5 parity bar of the float32 output).
+// The staging tile is free after pass 1: the next tile's TMA load overlaps passes 2 and 3.
+constexpr int kBoxCpl = 5;                 // cells per lane in the row scan
+constexpr int kBoxSW = 32 * kBoxCpl;       // table / staging row length (cells): compile-time strides
+constexpr int kBoxPad = 16;                // cells left of the tile (>= rx + 1, 64-byte aligned box start)
+constexpr int kBoxMaxK = 25;               // pad + 128 + rx <= kBoxSW and rx + 1 <= pad
+constexpr int kBoxThreads = 512;
+constexpr int kBoxTH = 32;                 // output rows per tile
+
+struct BoxGeom {
+    int H, W;      // raster (both < 2^31, checked by the caller)
+    int kh, kw, ry, rx;
+    int sh;        // table rows = kBoxTH + kh (row 0 is the row above the first window)
+    int tiles_x, tiles_y;
+    int box_h;     // rows per TMA box
+};
+
+__device__ __noinline__ float box_direct(const float *__restrict__ in, int64_t pitch_elems, int64_t y, int64_t x,
+                                         int kh, int kw, double w) {
+    double acc = 0.0;
+    const float *p = in + (y - kh / 2) * pitch_elems + (x - kw / 2);
+    for (int ky = 0; ky < kh && acc == acc; ++ky)
+        for (int kx = 0; kx < kw; ++kx) acc = fma(w, (double)p[ky * pitch_elems + kx], acc);
+    return (float)acc;
+}
+
+template <bool CHECK>
+__device__ __forceinline__ void box_column_prefix(const float *sp, double *dp, int sh, int r_lo, int r_n) {
+    double acc = 0.0;
+    int r = 0;
+    for (; r + 8 <= sh; r += 8, sp += 8 * kBoxSW, dp += 8 * kBoxSW) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = sp[u * kBoxSW];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool ok = !CHECK || (unsigned)(r + u - r_lo) < (unsigned)r_n;
+            acc += ok ? (double)v[u] : 0.0;
+            dp[u * kBoxSW] = acc;
+        }
+    }
+    for (; r < sh; ++r, sp += kBoxSW, dp += kBoxSW) {
+        const bool ok = !CHECK || (unsigned)(r - r_lo) < (unsigned)r_n;
+        acc += ok ? (double)sp[0] : 0.0;
+        dp[0] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(kBoxThreads)
+conv_box_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ in, int64_t in_pitch_elems,
+                float *__restrict__ out, int64_t out_pitch_elems, const BoxGeom g, const double w) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int nbox = (g.sh + g.box_h - 1) / g.box_h;
+    const int stage_rows = nbox * g.box_h;
+    float *stage = reinterpret_cast<float *>(smem_raw);                                  // rows of 640 B
+    double *S = reinterpret_cast<double *>(smem_raw + (size_t)stage_rows * kBoxSW * sizeof(float));
+    uint64_t *bar = reinterpret_cast<uint64_t *>(S + (size_t)g.sh * kBoxSW);
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap);
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_tiles = g.tiles_x * g.tiles_y;
+    auto issue = [&](int t) {  // thread 0 only
+        const int tile_y = t / g.tiles_x, tile_x = t - tile_y * g.tiles_x;
+        const int bx = tile_x * kTileW - kBoxPad, by = tile_y * kBoxTH - g.ry - 1;
+        mbar_arrive_expect_tx(bar, (uint32_t)(stage_rows * kBoxSW * sizeof(float)));
+        for (int b = 0; b < nbox; ++b)
+            tma_load_2d(stage + b * g.box_h * kBoxSW, &tmap, bar, bx, by + b * g.box_h);
+    };
+    if (threadIdx.x == 0 && (int)blockIdx.x < n_tiles) issue(blockIdx.x);
+
+    uint32_t parity = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int tile_y = t / g.tiles_x, tile_x = t - tile_y * g.tiles_x;
+        const int x0 = tile_x * kTileW, y0 = tile_y * kBoxTH;
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+
+        // pass 1: column prefix sums (8 loads in flight per thread, one add chain per column).
+        // Table row r is raster row y0 - ry - 1 + r: rows [r_lo, r_lo + r_n) lie inside the raster;
+        // tiles whose whole table does skip the per-cell test.
+        if (threadIdx.x < kBoxSW) {
+            const int c = threadIdx.x;
+            const int gx = x0 - kBoxPad + c;
+            const int r_lo = max(0, g.ry + 1 - y0);
+            const int r_n = (gx >= 0 && gx < g.W) ? max(0, min(g.sh, g.H - (y0 - g.ry - 1)) - r_lo) : 0;
+            const bool inside = (x0 >= kBoxPad) && (x0 - kBoxPad + kBoxSW <= g.W) && (y0 > g.ry) &&
+                                (y0 - g.ry - 1 + g.sh <= g.H);  // CTA-uniform
+            if (inside) box_column_prefix<false>(stage + c, S + c, g.sh, 0, 0);
+            else box_column_prefix<true>(stage + c, S + c, g.sh, r_lo, r_n);
+        }
+        __syncthreads();
+        // the float32 staging tile is dead: fetch the next tile behind passes 2 and 3
+        if (threadIdx.x == 0 && t + (int)gridDim.x < n_tiles) issue(t + gridDim.x);
+
+        // pass 2: row prefix sums, in place; a warp scans two rows at a time so that the shuffle
+        // chains of one row hide behind the other's
+        for (int r = warp * 2; r < g.sh; r += 2 * (kBoxThreads / 32)) {
+            const bool two = r + 1 < g.sh;
+            double *row0 = S + r * kBoxSW + lane * kBoxCpl;
+            double *row1 = two ? row0 + kBoxSW : row0;
+            double e[2][kBoxCpl], inc[2];
+#pragma unroll
+            for (int j = 0; j < kBoxCpl; ++j) e[0][j] = row0[j], e[1][j] = row1[j];
+#pragma unroll
+            for (int j = 1; j < kBoxCpl; ++j) e[0][j] += e[0][j - 1], e[1][j] += e[1][j - 1];
+            inc[0] = e[0][kBoxCpl - 1];
+            inc[1] = e[1][kBoxCpl - 1];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double u0 = __shfl_up_sync(0xffffffffu, inc[0], o);
+                const double u1 = __shfl_up_sync(0xffffffffu, inc[1], o);
+                if (lane >= o) inc[0] += u0, inc[1] += u1;
+            }
+            const double x0e = inc[0] - e[0][kBoxCpl - 1], x1e = inc[1] - e[1][kBoxCpl - 1];  // exclusive offsets
+#pragma unroll
+            for (int j = 0; j < kBoxCpl; ++j) row0[j] = e[0][j] + x0e;
+            if (two) {
+#pragma unroll
+                for (int j = 0; j < kBoxCpl; ++j) row1[j] = e[1][j] + x1e;
+            }
+        }
+        __syncthreads();
+
+        // pass 3: outputs.  Thread = (column, group of rows); the window of output row oy spans
+        // table rows oy (excluded) .. oy + kh and table columns left (excluded) .. right.
+        {
+            constexpr int kRowsPer = kBoxTH / (kBoxThreads / kTileW);
+            const int cx = threadIdx.x & (kTileW - 1), oy0 = (threadIdx.x / kTileW) * kRowsPer;
+            const int x = x0 + cx;
+            if (x < g.W) {
+                const double *top = S + oy0 * kBoxSW + (kBoxPad + cx - g.rx - 1);
+                const double *bot = top + g.kh * kBoxSW;
+                const int span = 2 * g.rx + 1;
+                double sum[kRowsPer];
+#pragma unroll
+                for (int i = 0; i < kRowsPer; ++i)
+                    sum[i] = (bot[i * kBoxSW + span] - bot[i * kBoxSW]) - (top[i * kBoxSW + span] - top[i * kBoxSW]);
+                // rows [v_lo, v_lo + v_n) of the tile are inside the raster and off the NaN ring
+                const int v_lo = max(0, g.ry - y0);
+                const int v_n = ((x >= g.rx) && (x < g.W - g.rx)) ? max(0, min(kBoxTH, g.H - g.ry - y0) - v_lo) : 0;
+                const int in_n = min(kBoxTH, g.H - y0);
+                float *op = out + (int64_t)(y0 + oy0) * out_pitch_elems + x;
+#pragma unroll
+                for (int i = 0; i < kRowsPer; ++i, op += out_pitch_elems) {
+                    const double res = w * sum[i] + 0.0;
+                    float f = (float)res;
+                    if (!((unsigned)(oy0 + i - v_lo) < (unsigned)v_n)) f = nan_of<float>();
+                    else if (!(fabs(res) <= 1.7976931348623157e308))
+                        f = box_direct(in, in_pitch_elems, y0 + oy0 + i, x, g.kh, g.kw, w);
+                    if (oy0 + i < in_n) __stcs(op, f);
+                }
+            }
+        }
+        __syncthreads();  // S is rebuilt by the next iteration
+    }
+}
+
 // Fallback for rasters TMA cannot describe: one thread per cell, bounds-checked loads.
 __global__ void __launch_bounds__(256)
 conv2d_direct_kernel(const float *__restrict__ in, int64_t in_pitch_elems, const __grid_constant__ ConvWeights cw,
@@ -256,6 +434,17 @@ __device__ __forceinline__ float focal_reduce(const Fetch &fetch, const MaskBits
 // window once (twice for var / std), loads 8 cells per 4-tap chunk with two LDS.128 and feeds
 // every (output row, tap) pair whose mask bit is set.  Taps are visited in row-major window
 // order for each output, so the float32 `sum` is bit-identical to np.nansum on the scratch.
+// One loaded window cell as the reducers see it: NaN test, f64 widening and the "skip NaN" masking
+// happen once per loaded cell, not once per (output, tap) use.
+struct FocalCell {
+    float v;      // raw value
+    float vz;     // value, 0 when NaN
+    double d;     // (double)value
+    double dz;    // (double)value, 0 when NaN
+    int one;      // 1 when not NaN
+    bool ok;
+};
+
 template <typename F>
 __device__ __forceinline__ void focal_sweep(const float *tile32, const MaskBits &mask, const TileGeom &g, int tx,
                                             int ty, F &&f) {
@@ -267,13 +456,15 @@ __device__ __forceinline__ void focal_sweep(const float *tile32, const MaskBits 
             const float4 q0 = *reinterpret_cast<const float4 *>(rowp + kb);
             const float4 q1 = *reinterpret_cast<const float4 *>(rowp + kb + 4);
             const float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-            // NaN test and f64 widening once per loaded cell, not once per (output, tap) use
-            bool ok[8];
-            double dv[8];
+            FocalCell cell[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                ok[i] = (v[i] == v[i]);
-                dv[i] = (double)v[i];
+                cell[i].v = v[i];
+                cell[i].ok = (v[i] == v[i]);
+                cell[i].vz = cell[i].ok ? v[i] : 0.f;
+                cell[i].d = (double)v[i];
+                cell[i].dz = (double)cell[i].vz;
+                cell[i].one = cell[i].ok ? 1 : 0;
             }
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
@@ -284,7 +475,7 @@ __device__ __forceinline__ void focal_sweep(const float *tile32, const MaskBits 
                         const int kx = kb + tt - g.off;
                         if (kx >= 0 && kx < g.kw && mask.m[ky * g.kw + kx]) {  // warp-uniform
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) f(r, c, v[c + tt], dv[c + tt], ok[c + tt]);
+                            for (int c = 0; c < 4; ++c) f(r, c, cell[c + tt]);
                         }
                     }
                 }
@@ -324,9 +515,9 @@ focal_stat_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) sum[r][c] = 0.0, cnt[r][c] = 0;
-            focal_sweep(tile32, mask, g, tx, ty, [&](int r, int c, float, double d, bool ok) {
-                sum[r][c] += ok ? d : 0.0;
-                cnt[r][c] += ok ? 1 : 0;
+            focal_sweep(tile32, mask, g, tx, ty, [&](int r, int c, const FocalCell &q) {
+                sum[r][c] += q.dz;
+                cnt[r][c] += q.one;
             });
             if constexpr (STAT == XRS_STAT_MEAN) {
 #pragma unroll
@@ -339,9 +530,9 @@ focal_stat_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 for (int r = 0; r < 4; ++r)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) sum[r][c] = sum[r][c] / (double)cnt[r][c], ssd[r][c] = 0.0;
-                focal_sweep(tile32, mask, g, tx, ty, [&](int r, int c, float, double dvv, bool ok) {
-                    const double d = dvv - sum[r][c];
-                    ssd[r][c] += ok ? d * d : 0.0;
+                focal_sweep(tile32, mask, g, tx, ty, [&](int r, int c, const FocalCell &q) {
+                    const double d = q.d - sum[r][c];
+                    ssd[r][c] += q.ok ? d * d : 0.0;
                 });
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
@@ -356,18 +547,17 @@ focal_stat_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) res[r][c] = 0.f;
-            focal_sweep(tile32, mask, g, tx, ty, [&](int r, int c, float v, double, bool ok) { res[r][c] += ok ? v : 0.f; });
+            focal_sweep(tile32, mask, g, tx, ty, [&](int r, int c, const FocalCell &q) { res[r][c] += q.vz; });
         } else {
             float mn[4][4], mx[4][4];
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) mn[r][c] = mx[r][c] = nan_of<float>();
-            focal_sweep(tile32, mask, g, tx, ty, [&](int r, int c, float v, double, bool ok) {
-                if (ok) {
-                    if (!(mn[r][c] < v)) mn[r][c] = v;
-                    if (!(mx[r][c] > v)) mx[r][c] = v;
-                }
+            // fminf / fmaxf return the non-NaN operand: exactly the NaN-skipping min / max
+            focal_sweep(tile32, mask, g, tx, ty, [&](int r, int c, const FocalCell &q) {
+                mn[r][c] = fminf(mn[r][c], q.v);
+                mx[r][c] = fmaxf(mx[r][c], q.v);
             });
 #pragma unroll
             for (int r = 0; r < 4; ++r)
@@ -382,6 +572,119 @@ focal_stat_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             if (yo < g.H && xo < g.W)  // W % 4 == 0 on this path
                 __stcs(reinterpret_cast<float4 *>(out + yo * out_pitch_elems + xo),
                        make_float4(res[r][0], res[r][1], res[r][2], res[r][3]));
+        }
+        __syncthreads();
+    }
+}
+
+// All requested statistics of one window in ONE pass over the raster (focal.focal_stats,
+// focal.py:800-878, is seven `apply` calls stacked with xr.concat): the tile is loaded once,
+// sweep A accumulates the float64 sum, the count and the float32 row-major sum of every output's
+// window, sweep B the min / max and the squared deviations about the float64 mean, and each
+// statistic goes straight into its plane of the (stats, y, x) result -- 2 sweeps and one tile
+// load instead of 9 and 7, and no stacking copy.  Per-statistic arithmetic is the single-stat
+// kernel's, operation for operation.
+struct StatPlanes {
+    float *p[7];  // indexed by xrs_focal_stat; nullptr = not requested
+};
+
+__device__ __forceinline__ void store_tile16(float *plane, int64_t pitch_elems, int64_t H, int64_t W, int64_t y0,
+                                             int64_t xo, const float (&res)[4][4]) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        if (y0 + r < H && xo < W)  // W % 4 == 0 on this path
+            __stcs(reinterpret_cast<float4 *>(plane + (y0 + r) * pitch_elems + xo),
+                   make_float4(res[r][0], res[r][1], res[r][2], res[r][3]));
+}
+
+__global__ void __launch_bounds__(256, 2)
+focal_stats_multi_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MaskBits mask,
+                         const StatPlanes planes, int64_t out_pitch_elems, const TileGeom g) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int nbox = (g.sh + g.box_h - 1) / g.box_h;
+    const size_t tile_cells = (size_t)nbox * g.box_h * g.sw;
+    float *tile32 = reinterpret_cast<float *>(smem_raw);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + tile_cells * sizeof(float));
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap);
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const bool want_b = planes.p[XRS_STAT_MIN] || planes.p[XRS_STAT_MAX] || planes.p[XRS_STAT_RANGE] ||
+                        planes.p[XRS_STAT_STD] || planes.p[XRS_STAT_VAR];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t n_tiles = (int64_t)g.tiles_x * g.tiles_y;
+    uint32_t parity = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int tile_y = (int)(t / g.tiles_x), tile_x = (int)(t % g.tiles_x);
+        const int x0 = tile_x * kTileW, y0 = tile_y * kTileH;
+        load_tile_tma(&tmap, tile32, bar, g, x0, y0, parity);
+        parity ^= 1u;
+        const int64_t xo = (int64_t)x0 + 4 * tx, yo = (int64_t)y0 + ty * 4;
+        float res[4][4];
+        double mean[4][4];
+        int cnt[4][4];
+        {
+            float fsum[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) mean[r][c] = 0.0, cnt[r][c] = 0, fsum[r][c] = 0.f;
+            focal_sweep(tile32, mask, g, tx, ty, [&](int r, int c, const FocalCell &q) {
+                mean[r][c] += q.dz;
+                cnt[r][c] += q.one;
+                fsum[r][c] += q.vz;
+            });
+            if (planes.p[XRS_STAT_SUM]) store_tile16(planes.p[XRS_STAT_SUM], out_pitch_elems, g.H, g.W, yo, xo, fsum);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    mean[r][c] = mean[r][c] / (double)cnt[r][c];
+                    res[r][c] = (float)mean[r][c];
+                }
+            if (planes.p[XRS_STAT_MEAN]) store_tile16(planes.p[XRS_STAT_MEAN], out_pitch_elems, g.H, g.W, yo, xo, res);
+        }
+        if (want_b) {
+            float mn[4][4], mx[4][4];
+            double ssd[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) mn[r][c] = mx[r][c] = nan_of<float>(), ssd[r][c] = 0.0;
+            focal_sweep(tile32, mask, g, tx, ty, [&](int r, int c, const FocalCell &q) {
+                const double d = q.d - mean[r][c];
+                ssd[r][c] += q.ok ? d * d : 0.0;
+                mn[r][c] = fminf(mn[r][c], q.v);
+                mx[r][c] = fmaxf(mx[r][c], q.v);
+            });
+            if (planes.p[XRS_STAT_MIN]) store_tile16(planes.p[XRS_STAT_MIN], out_pitch_elems, g.H, g.W, yo, xo, mn);
+            if (planes.p[XRS_STAT_MAX]) store_tile16(planes.p[XRS_STAT_MAX], out_pitch_elems, g.H, g.W, yo, xo, mx);
+            if (planes.p[XRS_STAT_RANGE]) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) res[r][c] = mx[r][c] - mn[r][c];
+                store_tile16(planes.p[XRS_STAT_RANGE], out_pitch_elems, g.H, g.W, yo, xo, res);
+            }
+            if (planes.p[XRS_STAT_VAR] || planes.p[XRS_STAT_STD]) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        ssd[r][c] = ssd[r][c] / (double)cnt[r][c];
+                        res[r][c] = (float)ssd[r][c];
+                    }
+                if (planes.p[XRS_STAT_VAR]) store_tile16(planes.p[XRS_STAT_VAR], out_pitch_elems, g.H, g.W, yo, xo, res);
+                if (planes.p[XRS_STAT_STD]) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) res[r][c] = (float)sqrt(ssd[r][c]);
+                    store_tile16(planes.p[XRS_STAT_STD], out_pitch_elems, g.H, g.W, yo, xo, res);
+                }
+            }
         }
         __syncthreads();
     }
@@ -431,6 +734,44 @@ static bool tile_geom(TileGeom &g, CUtensorMap *tmap, const float *in, int64_t i
     return make_tensor_map_2d(tmap, in, in_pitch, H, W, 4, g.sw, g.box_h);
 }
 
+// all taps bitwise equal (and finite), k <= 25 per side, TMA-describable raster: summed-area path
+static bool try_box(const float *in, int64_t in_pitch, float *out, int64_t out_pitch, int64_t H, int64_t W,
+                    const double *kernel, int kh, int kw, cudaStream_t s, int *rc) {
+    if (kh > kBoxMaxK || kw > kBoxMaxK) return false;
+    const double w = kernel[0];
+    if (!(fabs(w) <= 1.7976931348623157e308)) return false;
+    for (int i = 1; i < kh * kw; ++i)
+        if (memcmp(&kernel[i], &w, sizeof(double)) != 0) return false;
+    if (W % 4 != 0) return false;
+    BoxGeom g;
+    g.H = (int)H; g.W = (int)W; g.kh = kh; g.kw = kw; g.ry = kh / 2; g.rx = kw / 2;
+    g.sh = kBoxTH + kh;
+    g.tiles_x = (int)((W + kTileW - 1) / kTileW);
+    g.tiles_y = (int)((H + kBoxTH - 1) / kBoxTH);
+    if ((int64_t)g.tiles_x * g.tiles_y >= (1LL << 31)) return false;
+    g.box_h = g.sh <= 64 ? g.sh : 64;
+    static_assert(kBoxPad + kTileW + kBoxMaxK / 2 <= kBoxSW && kBoxMaxK / 2 + 1 <= kBoxPad, "box tile geometry");
+    CUtensorMap tmap;
+    if (!make_tensor_map_2d(&tmap, in, in_pitch, H, W, 4, kBoxSW, g.box_h)) return false;
+    const int nbox = (g.sh + g.box_h - 1) / g.box_h;
+    const size_t smem = (size_t)nbox * g.box_h * kBoxSW * 4 + (size_t)g.sh * kBoxSW * 8 + 16;
+    if (smem > 227 * 1024) return false;
+    *rc = XRS_OK;
+    cudaError_t e = cudaFuncSetAttribute(conv_box_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_box_kernel, kBoxThreads, smem);
+    if (e != cudaSuccess) { *rc = cuda_fail(e, "conv_box_kernel setup"); return true; }
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)sm_count() * per_sm;
+    const int64_t n_tiles = (int64_t)g.tiles_x * g.tiles_y;
+    if (grid > n_tiles) grid = n_tiles;
+    conv_box_kernel<<<(unsigned)grid, kBoxThreads, smem, s>>>(tmap, in, in_pitch / 4, out, out_pitch / 4, g, w);
+    last_launch_info() = {3, (int)grid, kBoxThreads, (int)smem};
+    e = cudaGetLastError();
+    if (e != cudaSuccess) *rc = cuda_fail(e, "conv_box_kernel launch");
+    return true;
+}
+
 }  // namespace xrs
 
 using namespace xrs;
@@ -446,6 +787,10 @@ int xrs_convolve2d_f32(const float *in, int64_t in_pitch, float *out, int64_t ou
     const int rc = check_common(in, in_pitch, out, out_pitch, H, W, kernel, kh, kw);
     if (rc) return rc;
     if (kh == 3 && kw == 3) return xrs_conv3_strip(in, in_pitch, out, out_pitch, H, W, kernel, (cudaStream_t)s);
+    {
+        int brc = XRS_OK;
+        if (try_box(in, in_pitch, out, out_pitch, H, W, kernel, kh, kw, (cudaStream_t)s, &brc)) return brc;
+    }
     static thread_local ConvWeights cw;
     for (int i = 0; i < kh * kw; ++i) cw.w[i] = kernel[i];
     TileGeom g;
@@ -464,6 +809,7 @@ int xrs_convolve2d_f32(const float *in, int64_t in_pitch, float *out, int64_t ou
             const int64_t n_tiles = (int64_t)g.tiles_x * g.tiles_y;
             if (grid > n_tiles) grid = n_tiles;
             conv2d_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)s>>>(tmap, cw, out, out_pitch / 4, g);
+            last_launch_info() = {4, (int)grid, 256, (int)smem};
             XRS_CUDA(cudaGetLastError());
             return XRS_OK;
         }
@@ -472,6 +818,7 @@ int xrs_convolve2d_f32(const float *in, int64_t in_pitch, float *out, int64_t ou
     if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
     conv2d_direct_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)s>>>(in, in_pitch / 4, cw, out, out_pitch / 4, H, W,
                                                                      kh, kw);
+    last_launch_info() = {5, (int)grid, 256, 0};
     XRS_CUDA(cudaGetLastError());
     return XRS_OK;
 }
@@ -491,18 +838,20 @@ int xrs_focal_stat_f32(const float *in, int64_t in_pitch, float *out, int64_t ou
         const int nbox = (g.sh + g.box_h - 1) / g.box_h;
         const size_t smem = (size_t)nbox * g.box_h * g.sw * 4 + 16;
         if (smem <= 227 * 1024) {
-            int per_sm = (int)((227 * 1024) / (smem + 1024));
-            if (per_sm > 3) per_sm = 3;
-            if (per_sm < 1) per_sm = 1;
-            int64_t grid = (int64_t)sms * per_sm;
             const int64_t n_tiles = (int64_t)g.tiles_x * g.tiles_y;
-            if (grid > n_tiles) grid = n_tiles;
+            // resident CTAs only (registers differ a lot between the statistics): the tile loop is persistent
 #define XRS_FS(ST)                                                                                              \
-    case ST:                                                                                                    \
+    case ST: {                                                                                                  \
         XRS_CUDA(cudaFuncSetAttribute(focal_stat_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                       (int)smem));                                                              \
+        int per_sm = 0;                                                                                         \
+        XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, focal_stat_kernel<ST>, 256, smem));    \
+        per_sm = per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm);                                                    \
+        int64_t grid = (int64_t)sms * per_sm;                                                                   \
+        if (grid > n_tiles) grid = n_tiles;                                                                     \
         focal_stat_kernel<ST><<<(unsigned)grid, 256, smem, (cudaStream_t)s>>>(tmap, mask, out, out_pitch / 4, g); \
-        break;
+        break;                                                                                                  \
+    }
             switch (stat) {
                 XRS_FS(XRS_STAT_MEAN) XRS_FS(XRS_STAT_SUM) XRS_FS(XRS_STAT_MIN) XRS_FS(XRS_STAT_MAX)
                 XRS_FS(XRS_STAT_STD) XRS_FS(XRS_STAT_RANGE) XRS_FS(XRS_STAT_VAR)
@@ -517,6 +866,52 @@ int xrs_focal_stat_f32(const float *in, int64_t in_pitch, float *out, int64_t ou
     focal_stat_direct_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)s>>>(in, in_pitch / 4, mask, out, out_pitch / 4,
                                                                          H, W, kh, kw, stat);
     XRS_CUDA(cudaGetLastError());
+    return XRS_OK;
+}
+
+int xrs_focal_stats_multi_f32(const float *in, int64_t in_pitch, float *out, int64_t out_pitch, int64_t plane_stride,
+                              int64_t H, int64_t W, const double *kernel, int kh, int kw, const int *stats,
+                              int n_stats, xrs_stream_t s) {
+    XRS_REQUIRE(stats != nullptr && n_stats >= 1 && n_stats <= 7, "stats: 1..7 statistic ids");
+    XRS_REQUIRE(plane_stride % 16 == 0 && plane_stride >= H * out_pitch, "plane_stride must cover one plane (16-byte multiple)");
+    if (H <= 0 || W <= 0) return XRS_OK;
+    const int rc = check_common(in, in_pitch, out, out_pitch, H, W, kernel, kh, kw);
+    if (rc) return rc;
+    StatPlanes planes;
+    for (auto &p : planes.p) p = nullptr;
+    for (int i = 0; i < n_stats; ++i) {
+        XRS_REQUIRE(stats[i] >= XRS_STAT_MEAN && stats[i] <= XRS_STAT_VAR, "unknown focal statistic");
+        XRS_REQUIRE(planes.p[stats[i]] == nullptr, "statistic requested twice");
+        planes.p[stats[i]] = reinterpret_cast<float *>(reinterpret_cast<char *>(out) + (int64_t)i * plane_stride);
+    }
+    TileGeom g;
+    CUtensorMap tmap;
+    if (n_stats >= 2 && tile_geom(g, &tmap, in, in_pitch, out, out_pitch, H, W, kh, kw, kTileH)) {
+        const int nbox = (g.sh + g.box_h - 1) / g.box_h;
+        const size_t smem = (size_t)nbox * g.box_h * g.sw * 4 + 16;
+        if (smem <= 227 * 1024) {
+            static thread_local MaskBits mask;
+            for (int i = 0; i < kh * kw; ++i) mask.m[i] = (kernel[i] == 1.0) ? 1 : 0;  // focal.py:323
+            XRS_CUDA(cudaFuncSetAttribute(focal_stats_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+            int per_sm = 0;
+            XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, focal_stats_multi_kernel, 256, smem));
+            if (per_sm < 1) per_sm = 1;
+            if (per_sm > 3) per_sm = 3;
+            int64_t grid = (int64_t)sm_count() * per_sm;
+            const int64_t n_tiles = (int64_t)g.tiles_x * g.tiles_y;
+            if (grid > n_tiles) grid = n_tiles;
+            focal_stats_multi_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)s>>>(tmap, mask, planes, out_pitch / 4, g);
+            XRS_CUDA(cudaGetLastError());
+            last_launch_info() = {6, (int)grid, 256, (int)smem};
+            return XRS_OK;
+        }
+    }
+    // single statistic, or a raster TMA cannot describe: one launch per plane
+    for (int i = 0; i < n_stats; ++i) {
+        const int r2 = xrs_focal_stat_f32(in, in_pitch, planes.p[stats[i]], out_pitch, H, W, kernel, kh, kw, stats[i], s);
+        if (r2) return r2;
+    }
     return XRS_OK;
 }
 

@@ -129,7 +129,7 @@ int xrs_host_free(void *ptr) {
     XRS_CUDA(cudaFreeHost(ptr));
     return XRS_OK;
 }
-// test hook: 1 if the last stencil launch on this thread used the TMA kernel
+// test hook: which kernel the last launch on this thread chose (codes in xrs_b200.h)
 int xrs_debug_last_used_tma(void) { return xrs::last_launch_info().used_tma; }
 int xrs_debug_last_grid(void) { return xrs::last_launch_info().grid; }
 

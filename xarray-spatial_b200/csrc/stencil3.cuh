@@ -364,11 +364,6 @@ stencil3_cpasync_kernel(const typename Op::in_t *__restrict__ in, int64_t in_pit
 }
 
 // ----------------------------------------------------------------------------- host launcher
-struct LaunchInfo {  // for tests / profiling: what the last launch chose
-    int used_tma;
-    int grid, block, smem_bytes;
-};
-LaunchInfo &last_launch_info();
 
 template <typename Op, int ROWS, int STAGES>
 int launch_stencil3(const typename Op::in_t *in, int64_t in_pitch_bytes, const typename Op::Params &prm,

@@ -5,6 +5,7 @@ arbitrary Python/Numba callable cannot cross the C ABI (SURVEY.md section 2 row 
 `hotspots` = convolve_2d + global mean/std + an int8 classification.
 """
 import ctypes
+from collections import OrderedDict
 
 import numpy as np
 import pandas as pd
@@ -139,6 +140,25 @@ def apply(raster, kernel, func=_calc_mean, name='focal_apply'):
     return DataArray(out, name=name, coords=raster.coords, dims=raster.dims, attrs=raster.attrs)
 
 
+def _focal_stats_cupy(data, kernel, stats_funcs):
+    """device raster -> (stats, y, x) stack from ONE pass (xrs_focal_stats_multi_f32); replaces
+    focal.py:757 `_focal_stats_cupy`, with the CPU (NaN-skipping, kernel == 1) semantics."""
+    import torch
+    from .utils import device_f32_2d, stream_ptr
+    t = device_f32_2d(data)
+    H, W = t.shape
+    k = np.ascontiguousarray(kernel, dtype=np.float64)
+    ids = (ctypes.c_int * len(stats_funcs))(*[_lib.STATS[s] for s in stats_funcs])
+    out = torch.empty((len(stats_funcs), H, W), dtype=torch.float32, device=t.device)
+    if H and W:
+        with torch.cuda.device(t.device):
+            _lib.call("xrs_focal_stats_multi_f32", ctypes.c_void_p(t.data_ptr()), t.stride(0) * 4,
+                      ctypes.c_void_p(out.data_ptr()), out.stride(1) * 4, out.stride(0) * 4, H, W,
+                      k.ctypes.data_as(ctypes.c_void_p), k.shape[0], k.shape[1], ids, len(stats_funcs),
+                      stream_ptr(t))
+    return like_container(out, data)
+
+
 def focal_stats(agg, kernel, stats_funcs=['mean', 'max', 'min', 'range', 'std', 'var', 'sum']):
     """Stack of focal statistics along a new 'stats' dimension (focal.py:800-878)."""
     if not isinstance(agg, DataArray):
@@ -146,12 +166,22 @@ def focal_stats(agg, kernel, stats_funcs=['mean', 'max', 'min', 'range', 'std', 
     if agg.ndim != 2:
         raise ValueError("`agg` must be 2D")
     kernel = custom_kernel(kernel)
-    stats_aggs = []
     for stats in stats_funcs:
         if stats not in _REDUCERS:
             raise ValueError("unknown focal statistic %r" % (stats,))
-        stats_aggs.append(apply(agg, kernel, func=_REDUCERS[stats]))
-    return concat(stats_aggs, pd.Index(stats_funcs, name='stats', dtype=object))
+    stats_funcs = list(stats_funcs)
+    index = pd.Index(stats_funcs, name='stats', dtype=object)
+    if is_device_array(agg.data) and len(set(stats_funcs)) == len(stats_funcs) and 2 <= len(stats_funcs) <= 7 \
+            and agg.shape[1] % 4 == 0:
+        # one fused pass writing straight into the stacked result
+        data = _focal_stats_cupy(agg.data, kernel, stats_funcs)
+        coords = OrderedDict()
+        coords['stats'] = np.asarray(stats_funcs, dtype=object)
+        coords.update(agg.coords)
+        return DataArray(data, coords=coords, dims=('stats',) + tuple(agg.dims), attrs=agg.attrs,
+                         name='focal_apply')
+    stats_aggs = [apply(agg, kernel, func=_REDUCERS[stats]) for stats in stats_funcs]
+    return concat(stats_aggs, index)
 
 
 # ----------------------------------------------------------------------------- hotspots
