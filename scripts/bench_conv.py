@@ -33,7 +33,7 @@ for k in (5, 9, 15, 25):
     print("uniform k=%2d : %8.3f ms  %7.1f Gcells/s  path=%d" % (k, ms, dem.numel() / ms / 1e6,
                                                                  xb._lib.lib().xrs_debug_last_used_tma()), flush=True)
 sub = dem[: side // 8]
-for k in (9, 25):
+for k in (5, 7, 9, 11, 13, 15, 25):
     kern = rng.standard_normal((k, k))
     ms = timeit(lambda: convolve_2d(sub, kern), n=3)
     print("mixed   k=%2d : %8.3f ms  %7.1f Gcells/s  path=%d" % (k, ms, sub.numel() / ms / 1e6,

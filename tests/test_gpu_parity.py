@@ -210,7 +210,7 @@ def test_host_path_chunked_rows_invariant(xb):
     assert_close_f32(got, ref, atol=1e-6 * np.nanmax(np.abs(ref)), what="host convolve")
 
 
-@pytest.mark.parametrize("k", [3, 9, 25])
+@pytest.mark.parametrize("k", [3, 5, 7, 9, 11, 13, 15, 25])
 def test_convolve_sizes_vs_oracle(xb, k):
     from xrspatial_b200.convolution import convolve_2d
     rng = np.random.default_rng(k)

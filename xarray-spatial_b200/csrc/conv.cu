@@ -59,6 +59,9 @@ __device__ __forceinline__ void load_tile_tma(const CUtensorMap *tmap, float *ti
 // accumulators per thread give the FP64 pipe enough parallelism at 2-3 CTAs per SM.
 constexpr int kConvTileH = 64;
 
+// KW > 0: kernel width known at compile time (5, 7, 9: the usual custom kernels) -- the tap-chunk
+// loop unrolls and its chunk / tap tests fold away; KW == 0: any odd shape.
+template <int KW>
 __global__ void __launch_bounds__(256)
 conv2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ConvWeights cw,
               float *__restrict__ out, int64_t out_pitch_elems, const TileGeom g) {
@@ -96,11 +99,14 @@ conv2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
         // rows / edge chunks take the generic, predicated path.  Taps are indexed from the
         // 16-byte aligned tile origin: tap kx sits at column kx + off.
         const int rows_in = 4 + g.kh - 1;
-        const int n_taps = g.off + g.kw;
+        constexpr int kOffC = KW ? ((KW / 2 + 3) / 4 * 4 - KW / 2) : 0;
+        const int kw = KW ? KW : g.kw;
+        const int off = KW ? kOffC : g.off;
+        const int n_taps = off + kw;
         for (int j = 0; j < rows_in; ++j) {
             const float *rowp = tile32 + (size_t)(ty * 4 + j) * g.sw + 4 * tx;
             const bool full_rows = (j >= 3) && (j < g.kh);
-            for (int kb = 0; kb < n_taps; kb += 4) {
+            auto chunk = [&](const int kb) {
                 const float4 a0 = *reinterpret_cast<const float4 *>(rowp + kb);
                 const float4 a1 = *reinterpret_cast<const float4 *>(rowp + kb + 4);
                 const float4 b0 = *reinterpret_cast<const float4 *>(rowp + 64 + kb);
@@ -109,12 +115,12 @@ conv2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
                                       (double)a1.x, (double)a1.y, (double)a1.z, (double)a1.w};
                 const double vb[8] = {(double)b0.x, (double)b0.y, (double)b0.z, (double)b0.w,
                                       (double)b1.x, (double)b1.y, (double)b1.z, (double)b1.w};
-                const bool full_chunk = (kb >= g.off) && (kb + 4 <= n_taps);
+                const bool full_chunk = (kb >= off) && (kb + 4 <= n_taps);
                 if (full_chunk && full_rows) {
-                    const double *w0 = cw.w + (j * g.kw + kb - g.off);  // kernel row j, taps kb-off ..
+                    const double *w0 = cw.w + (j * kw + kb - off);  // kernel row j, taps kb-off ..
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const double *wr = w0 - r * g.kw;            // kernel row j - r
+                        const double *wr = w0 - r * kw;            // kernel row j - r
 #pragma unroll
                         for (int tt = 0; tt < 4; ++tt) {
                             const double wv = wr[tt];
@@ -127,11 +133,11 @@ conv2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
                     }
                 } else if (full_chunk) {
                     // lead-in / lead-out rows of the window: some output rows have no kernel row here
-                    const double *w0 = cw.w + (j * g.kw + kb - g.off);
+                    const double *w0 = cw.w + (j * kw + kb - off);
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         if (j - r >= 0 && j - r < g.kh) {  // warp-uniform
-                            const double *wr = w0 - r * g.kw;        // kernel row j - r
+                            const double *wr = w0 - r * kw;        // kernel row j - r
 #pragma unroll
                             for (int tt = 0; tt < 4; ++tt) {
                                 const double wv = wr[tt];
@@ -150,9 +156,9 @@ conv2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
                         if (ky >= 0 && ky < g.kh) {
 #pragma unroll
                             for (int tt = 0; tt < 4; ++tt) {
-                                const int kx = kb + tt - g.off;
-                                if (kx >= 0 && kx < g.kw) {
-                                    const double wv = cw.w[ky * g.kw + kx];
+                                const int kx = kb + tt - off;
+                                if (kx >= 0 && kx < kw) {
+                                    const double wv = cw.w[ky * kw + kx];
 #pragma unroll
                                     for (int c = 0; c < 4; ++c) {
                                         acc[r][c] = fma(wv, va[c + tt], acc[r][c]);
@@ -163,6 +169,12 @@ conv2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
                         }
                     }
                 }
+            };
+            if constexpr (KW > 0) {
+#pragma unroll
+                for (int kb = 0; kb < kOffC + KW; kb += 4) chunk(kb);
+            } else {
+                for (int kb = 0; kb < n_taps; kb += 4) chunk(kb);
             }
         }
         const int64_t xa = (int64_t)x0 + 4 * tx, xb = xa + 64;
@@ -180,6 +192,87 @@ conv2d_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
             }
         }
         __syncthreads();  // the tile buffer is reused by the next iteration
+    }
+}
+
+// Square K x K kernels with K in {5, 7, ..., 13} (the usual hand-made filters; at K = 15 the
+// unrolled code no longer fits the instruction cache and the looped kernel is faster): everything is unrolled,
+// so each loaded cell is widened to float64 once per row (not once per tap chunk) and every
+// weight is an immediate constant-bank operand of its DFMA.  Same tile / thread layout and
+// the same per-output accumulation order (row-major taps) as conv2d_kernel.
+template <int K>
+__global__ void __launch_bounds__(256, 2)
+conv2d_fixed_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ConvWeights cw,
+                    float *__restrict__ out, int64_t out_pitch_elems, const TileGeom g) {
+    constexpr int kOff = (K / 2 + 3) / 4 * 4 - K / 2;   // column of tap 0 relative to the aligned origin
+    constexpr int kVals = (kOff + K + 3 + 3) / 4 * 4;   // cells a thread needs per row and half
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int nbox = (g.sh + g.box_h - 1) / g.box_h;
+    const size_t tile_cells = (size_t)nbox * g.box_h * g.sw;
+    float *tile32 = reinterpret_cast<float *>(smem_raw);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + tile_cells * sizeof(float));
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap);
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int64_t n_tiles = (int64_t)g.tiles_x * g.tiles_y;
+    uint32_t parity = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int tile_y = (int)(t / g.tiles_x), tile_x = (int)(t % g.tiles_x);
+        const int x0 = tile_x * kTileW, y0 = tile_y * kConvTileH;
+        load_tile_tma(&tmap, tile32, bar, g, x0, y0, parity);
+        parity ^= 1u;
+        double acc[4][8];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[r][c] = 0.0;
+        const float *base = tile32 + (size_t)(ty * 4) * g.sw + 4 * tx;
+#pragma unroll
+        for (int j = 0; j < K + 3; ++j) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const float *rowp = base + (size_t)j * g.sw + half * 64;
+                double d[kVals];
+#pragma unroll
+                for (int q = 0; q < kVals / 4; ++q) {
+                    const float4 f = *reinterpret_cast<const float4 *>(rowp + 4 * q);
+                    d[4 * q + 0] = (double)f.x; d[4 * q + 1] = (double)f.y;
+                    d[4 * q + 2] = (double)f.z; d[4 * q + 3] = (double)f.w;
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int ky = j - r;
+                    if (ky >= 0 && ky < K) {
+#pragma unroll
+                        for (int kx = 0; kx < K; ++kx) {
+                            const double wv = cw.w[ky * K + kx];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                acc[r][half * 4 + c] = fma(wv, d[c + kx + kOff], acc[r][half * 4 + c]);
+                        }
+                    }
+                }
+            }
+        }
+        const int64_t xa = (int64_t)x0 + 4 * tx, xb = xa + 64;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int64_t yo = (int64_t)y0 + ty * 4 + r;
+            if (yo < g.H) {
+                float *orow = out + yo * out_pitch_elems;
+                if (xa < g.W)
+                    __stcs(reinterpret_cast<float4 *>(orow + xa),
+                           make_float4((float)acc[r][0], (float)acc[r][1], (float)acc[r][2], (float)acc[r][3]));
+                if (xb < g.W)
+                    __stcs(reinterpret_cast<float4 *>(orow + xb),
+                           make_float4((float)acc[r][4], (float)acc[r][5], (float)acc[r][6], (float)acc[r][7]));
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -801,16 +894,49 @@ int xrs_convolve2d_f32(const float *in, int64_t in_pitch, float *out, int64_t ou
         const size_t cells = (size_t)nbox * g.box_h * g.sw;
         const size_t smem = cells * 4 + 16;
         if (smem <= 227 * 1024) {
-            XRS_CUDA(cudaFuncSetAttribute(conv2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int per_sm = 0;
-            XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv2d_kernel, 256, smem));
-            if (per_sm < 1) per_sm = 1;
-            int64_t grid = (int64_t)sms * per_sm;
             const int64_t n_tiles = (int64_t)g.tiles_x * g.tiles_y;
-            if (grid > n_tiles) grid = n_tiles;
-            conv2d_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)s>>>(tmap, cw, out, out_pitch / 4, g);
-            last_launch_info() = {4, (int)grid, 256, (int)smem};
+            int64_t grid = 0;
+#define XRS_CONV(KWC)                                                                                          \
+    {                                                                                                          \
+        XRS_CUDA(cudaFuncSetAttribute(conv2d_kernel<KWC>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                      (int)smem));                                                             \
+        int per_sm = 0;                                                                                        \
+        XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv2d_kernel<KWC>, 256, smem));      \
+        if (per_sm < 1) per_sm = 1;                                                                            \
+        grid = (int64_t)sms * per_sm;                                                                          \
+        if (grid > n_tiles) grid = n_tiles;                                                                    \
+        conv2d_kernel<KWC><<<(unsigned)grid, 256, smem, (cudaStream_t)s>>>(tmap, cw, out, out_pitch / 4, g);  \
+    }
+#define XRS_CONVF(KC)                                                                                           \
+    {                                                                                                          \
+        XRS_CUDA(cudaFuncSetAttribute(conv2d_fixed_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                      (int)smem));                                                             \
+        int per_sm = 0;                                                                                        \
+        XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv2d_fixed_kernel<KC>, 256, smem)); \
+        if (per_sm < 1) per_sm = 1;                                                                            \
+        grid = (int64_t)sms * per_sm;                                                                          \
+        if (grid > n_tiles) grid = n_tiles;                                                                    \
+        conv2d_fixed_kernel<KC><<<(unsigned)grid, 256, smem, (cudaStream_t)s>>>(tmap, cw, out, out_pitch / 4, g); \
+    }
+            if (kh == kw && kw >= 5 && kw <= 13) {
+                switch (kw) {
+                    case 5: XRS_CONVF(5) break;
+                    case 7: XRS_CONVF(7) break;
+                    case 11: XRS_CONVF(11) break;
+                    case 13: XRS_CONVF(13) break;
+                    default: XRS_CONVF(9) break;
+                }
+            } else
+            switch (kw) {
+                case 5: XRS_CONV(5) break;
+                case 7: XRS_CONV(7) break;
+                case 9: XRS_CONV(9) break;
+                default: XRS_CONV(0) break;
+            }
+#undef XRS_CONV
+#undef XRS_CONVF
             XRS_CUDA(cudaGetLastError());
+            last_launch_info() = {4, (int)grid, 256, (int)smem};
             return XRS_OK;
         }
     }
