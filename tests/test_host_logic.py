@@ -86,6 +86,12 @@ def test_error_types_before_any_device_work():
     with pytest.raises(NotImplementedError):
         focal.apply(r, np.ones((3, 3)), func=lambda x: 0)    # only built-in reducers cross the C ABI
     with pytest.raises(ValueError):
+        focal.focal_stats(r, np.ones((3, 3)), stats_funcs=["mean", "median"])   # validated before any launch
+    with pytest.raises(TypeError):
+        focal.focal_stats(np.zeros((4, 4)), np.ones((3, 3)))
+    with pytest.raises(ValueError):
+        focal.focal_stats(r, np.ones((3, 4)))
+    with pytest.raises(ValueError):
         xb.savi(r, r, soil_factor=1.5)                       # multispectral.py:999-1000
     with pytest.raises(ValueError):
         xb.evi(r, r, r, gain=-1)
