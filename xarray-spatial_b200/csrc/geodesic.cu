@@ -4,9 +4,10 @@
 // u = A e + B n; slope = atan(|(A, B)|), aspect = atan2(-A, -B).  All float64, float32 output.
 //
 // Regular grids (1-D lat per row, 1-D lon per column -- the common case, utils.py:644-649) first
-// build two small trig tables (sin/cos lat and the prime-vertical radius N per row, sin/cos lon
-// per column), so a cell needs no transcendental except the final atan / atan2: ~300 FP64
-// operations per cell, FP64-bound.  Curvilinear grids (2-D lat/lon) evaluate the trig per
+// build two small trig tables (sin/cos lat and the prime-vertical radius N per row, sin/cos lon and
+// of the step to the next column per column), so a cell needs no transcendental except the final
+// atan / atan2, and the ECEF -> East/North/Up rotation is folded algebraically (see the kernel):
+// ~230 FP64 operations per cell, FP64-bound.  Curvilinear grids (2-D lat/lon) evaluate the trig per
 // neighbour.  One thread per output cell; the 27 loads hit L1/L2.
 #include <math.h>
 
@@ -20,8 +21,8 @@ constexpr double kInv2R = 1.0 / (2.0 * 6370994.884953014);  // geodesic.py:183
 constexpr double kDeg2Rad = 3.141592653589793 / 180.0;
 constexpr double kRad2Deg = 180.0 / 3.141592653589793;
 
-struct RowTrig { double s, c, n; };   // sin(lat), cos(lat), N(lat)
-struct ColTrig { double s, c; };      // sin(lon), cos(lon)
+struct RowTrig { double s, c, n, m; };     // sin(lat), cos(lat), N(lat), (b^2 / a^2) N(lat)
+struct ColTrig { double s, c, sd, cd; };   // sin(lon), cos(lon), sin / cos of (lon[x+1] - lon[x])
 
 __global__ void geo_tables_kernel(const double *lat, const double *lon, int64_t H, int64_t W, RowTrig *rt,
                                   ColTrig *ct) {
@@ -29,11 +30,15 @@ __global__ void geo_tables_kernel(const double *lat, const double *lon, int64_t 
     if (i < H) {
         const double r = lat[i] * kDeg2Rad, s = sin(r), c = cos(r);
         rt[i].s = s; rt[i].c = c;
-        rt[i].n = kA2 / sqrt(kA2 * c * c + kB2 * s * s);
+        const double nn = kA2 / sqrt(kA2 * c * c + kB2 * s * s);
+        rt[i].n = nn;
+        rt[i].m = kB2 / kA2 * nn;
     }
     if (i < W) {
         const double r = lon[i] * kDeg2Rad;
         ct[i].s = sin(r); ct[i].c = cos(r);
+        const double d = (i + 1 < W) ? (lon[i + 1] - lon[i]) * kDeg2Rad : 0.0;
+        ct[i].sd = sin(d); ct[i].cd = cos(d);
     }
 }
 
@@ -69,6 +74,43 @@ __global__ void __launch_bounds__(256) geodesic_kernel(const __grid_constant__ G
                     ok = ok && (v == v);
                 }
             if (ok) {
+                double Se = 0.0, Sn = 0.0, Su = 0.0, See = 0.0, Snn = 0.0, Sen = 0.0, Seu = 0.0, Snu = 0.0;
+                if constexpr (!GRID2D) {
+                    // Regular grid.  With t = (N + h) cos(lat), Z = (b^2/a^2 N + h) sin(lat) and
+                    // D = lon_k - lon_c, rotating the ECEF offset into the centre's frame collapses to
+                    //   e = t_k sin D,  p = t_k cos D - t_c,  w = Z_k - Z_c,
+                    //   n = cos(lat_c) w - sin(lat_c) p,  u = cos(lat_c) p + sin(lat_c) w
+                    // (the same quantities as geodesic.py:60-118 forms through X, Y, Z: ~23 FP64
+                    // operations per neighbour instead of ~36, none for e in the centre's column).
+                    const RowTrig rows[3] = {a.rt[y - 1], a.rt[y], a.rt[y + 1]};
+                    const ColTrig cl = a.ct[x - 1], cm = a.ct[x];
+                    const double sdl = -cl.sd, cdl = cl.cd, sdr = cm.sd, cdr = cm.cd;
+                    const double sc = rows[1].s, cc_ = rows[1].c;
+                    const double hc = h9[4] * a.z_factor;
+                    const double tc = (rows[1].n + hc) * cc_, Zc = (rows[1].m + hc) * sc;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        if (k == 4) continue;  // the centre contributes e = n = u = 0
+                        const RowTrig &r = rows[k / 3];
+                        const int dxk = k % 3;
+                        const double h = h9[k] * a.z_factor;
+                        const double t = (r.n + h) * r.c, Z = (r.m + h) * r.s;
+                        const double q = dxk == 1 ? t : t * (dxk == 0 ? cdl : cdr);
+                        const double pk = q - tc, wk = Z - Zc;
+                        const double nk = fma(cc_, wk, -(sc * pk));
+                        double uk = fma(cc_, pk, sc * wk);
+                        if (dxk == 1) {
+                            uk = fma(nk * nk, kInv2R, uk);
+                        } else {
+                            const double ek = t * (dxk == 0 ? sdl : sdr);
+                            uk = fma(fma(ek, ek, nk * nk), kInv2R, uk);
+                            Se += ek;
+                            See = fma(ek, ek, See); Sen = fma(ek, nk, Sen); Seu = fma(ek, uk, Seu);
+                        }
+                        Sn += nk; Su += uk;
+                        Snn = fma(nk, nk, Snn); Snu = fma(nk, uk, Snu);
+                    }
+                } else {
                 // centre cell first (it defines the local frame), then one neighbour at a time:
                 // ECEF -> offset -> (e, n, u) -> running sums of the normal equations.  The sums are
                 // accumulated uncentred and centred at the end (sum(de*du) = sum(e*u) - 9*me*mu);
@@ -76,16 +118,11 @@ __global__ void __launch_bounds__(256) geodesic_kernel(const __grid_constant__ G
                 RowTrig rc;
                 ColTrig cc;
                 auto trig = [&](int dy, int dx, RowTrig &r, ColTrig &c) {
-                    if constexpr (!GRID2D) {
-                        r = a.rt[y + dy - 1];
-                        c = a.ct[x + dx - 1];
-                    } else {
-                        const int64_t j = (y + dy - 1) * a.W + x + dx - 1;
-                        const double la = a.lat[j] * kDeg2Rad, lo = a.lon[j] * kDeg2Rad;
-                        r.s = sin(la); r.c = cos(la);
-                        r.n = kA2 / sqrt(kA2 * r.c * r.c + kB2 * r.s * r.s);
-                        c.s = sin(lo); c.c = cos(lo);
-                    }
+                    const int64_t j = (y + dy - 1) * a.W + x + dx - 1;
+                    const double la = a.lat[j] * kDeg2Rad, lo = a.lon[j] * kDeg2Rad;
+                    r.s = sin(la); r.c = cos(la);
+                    r.n = kA2 / sqrt(kA2 * r.c * r.c + kB2 * r.s * r.s);
+                    c.s = sin(lo); c.c = cos(lo);
                 };
                 auto ecef = [&](const RowTrig &r, const ColTrig &c, double h, double &X, double &Y, double &Z) {
                     const double t = (r.n + h) * r.c;
@@ -99,7 +136,6 @@ __global__ void __launch_bounds__(256) geodesic_kernel(const __grid_constant__ G
                 const double ex = -cc.s, ey = cc.c;
                 const double nx = -rc.s * cc.c, ny = -rc.s * cc.s, nz = rc.c;
                 const double ux = rc.c * cc.c, uy = rc.c * cc.s, uz = rc.s;
-                double Se = 0.0, Sn = 0.0, Su = 0.0, See = 0.0, Snn = 0.0, Sen = 0.0, Seu = 0.0, Snu = 0.0;
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {
                     if (k == 4) continue;  // the centre contributes e = n = u = 0
@@ -116,6 +152,7 @@ __global__ void __launch_bounds__(256) geodesic_kernel(const __grid_constant__ G
                     Se += ek; Sn += nk; Su += uk;
                     See = fma(ek, ek, See); Snn = fma(nk, nk, Snn); Sen = fma(ek, nk, Sen);
                     Seu = fma(ek, uk, Seu); Snu = fma(nk, uk, Snu);
+                }
                 }
                 const double me = Se * (1.0 / 9.0), mn = Sn * (1.0 / 9.0), mu = Su * (1.0 / 9.0);
                 See -= 9.0 * me * me; Snn -= 9.0 * mn * mn; Sen -= 9.0 * me * mn;
