@@ -116,6 +116,18 @@ hz = ((torch.arange(side, device="cuda", dtype=torch.int64)[:, None] * 7919 +
        torch.arange(side, device="cuda", dtype=torch.int64)[None, :] * 104729) % 1024).to(torch.int32)
 add("zonal hash partials, scattered zones", timeit(lambda: Z.hash_partials(hz, vt), n=3), 8,
     note="worst case: zone changes every cell")
+# next-tier rows: hotspots, majority, crosstab
+from xrspatial_b200.convolution import circle_kernel  # noqa: E402
+hsub = xb.DataArray(dem[: side // 4], dims=("y", "x"))
+ck = circle_kernel(1, 1, 2)
+add("hotspots, circle kernel r=2 (5x5)", timeit(lambda: xb.hotspots(hsub, ck), n=3), 5, ncells=hsub.data.numel(),
+    note="convolve + global mean/std + int8 classification")
+cats = ((dem * (16.0 / 4000.0)).floor().clamp_(0, 15)).contiguous()
+cagg = A(cats)
+add("zonal.crosstab 1024 zones x 16 classes", timeit(lambda: xb.zonal_crosstab(zagg, cagg), n=3), 8,
+    note="xrs_zonal_pair_count + host pivot")
+add("zonal.stats majority, 16 classes", timeit(lambda: xb.zonal_stats(zagg, cagg, stats_funcs=["majority"]), n=3), 8,
+    note="hash partials + pair histogram")
 out = os.path.join(ROOT, "gpurun_out", "ops.json")
 os.makedirs(os.path.dirname(out), exist_ok=True)
 json.dump(dict(side=side, peak_gbs=peak, rows=rows), open(out, "w"), indent=1)

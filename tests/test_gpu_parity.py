@@ -266,6 +266,33 @@ def test_convolve_box_path_small_and_ragged_rasters(xb):
     assert_close_f32(got, o.convolve_2d(z, kern, nthreads=4), atol=1e-6 * 4000.0, what="box 9x9 ragged")
 
 
+def test_focal_stats_multi_abi_ragged_width_falls_back_per_plane(xb):
+    """xrs_focal_stats_multi_f32 called directly on a raster TMA cannot describe (W % 4 != 0): the C
+    side serves it plane by plane with the bounds-checked kernel; same values as the oracle."""
+    import ctypes
+    from xrspatial_b200 import _lib
+    rng = np.random.default_rng(5)
+    z = terrain(rng, 37, 131, nans=0.02)
+    t = dev(z)
+    kern = np.ones((3, 3))
+    names = ["sum", "mean", "max"]
+    ids = (ctypes.c_int * 3)(*[_lib.STATS[n] for n in names])
+    # plane stride must be a 16-byte multiple covering one plane: use a padded buffer
+    stride = (37 * 131 * 4 + 15) // 16 * 16
+    buf = torch.empty(3 * stride // 4, dtype=torch.float32, device="cuda")
+    _lib.call("xrs_focal_stats_multi_f32", ctypes.c_void_p(t.data_ptr()), 131 * 4, ctypes.c_void_p(buf.data_ptr()),
+              131 * 4, stride, 37, 131, kern.ctypes.data_as(ctypes.c_void_p), 3, 3, ids, 3,
+              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    for i, n in enumerate(names):
+        got = buf[i * stride // 4: i * stride // 4 + 37 * 131].reshape(37, 131).cpu().numpy()
+        assert_close_f32(got, o.focal_apply(z, kern, n, nthreads=4), what="multi fallback " + n)
+    with pytest.raises(ValueError):
+        _lib.call("xrs_focal_stats_multi_f32", ctypes.c_void_p(t.data_ptr()), 131 * 4, ctypes.c_void_p(buf.data_ptr()),
+                  131 * 4, stride, 37, 131, kern.ctypes.data_as(ctypes.c_void_p), 3, 3,
+                  (ctypes.c_int * 2)(0, 0), 2, None)            # a statistic requested twice
+
+
 def test_focal_stats_tma_vs_oracle(xb):
     from xrspatial_b200 import focal
     from xrspatial_b200.convolution import circle_kernel

@@ -167,3 +167,29 @@ def test_split_rows():
     from xrspatial_b200.stripes import split_rows
     assert split_rows(10, 3) == [(0, 4), (4, 7), (7, 10)]
     assert split_rows(65536, 8)[7] == (57344, 65536)
+
+
+def test_crosstab_pivot_matches_pair_loop():
+    """The vectorised pivot of zonal.crosstab against the obvious loop (incl. a category subset,
+    unselected zones and a zone listed twice)."""
+    rng = np.random.default_rng(3)
+    pz = rng.integers(0, 40, 3000).astype(np.int64)
+    pv = rng.integers(0, 12, 3000).astype(np.float64)
+    pc = rng.integers(1, 1 << 20, 3000).astype(np.int64)
+    for sel, cats in ((np.arange(40), list(range(12))), (np.array([7, 3, 3, 39, 12]), [2.0, 5.0, 11.0]),
+                      (np.array([1.5, 2.0]), [0.0]), (np.array([], dtype=np.int64), [1.0])):
+        total, counts = zonal._pivot_pairs(sel, cats, pz, pv, pc)
+        zpos = {float(z): i for i, z in enumerate(sel)}
+        t2 = np.zeros(len(sel), np.float32)
+        c2 = np.zeros((len(cats), len(sel)), np.int64)
+        bounds = np.asarray(cats, dtype=np.float64)
+        for z, v, c in zip(pz.tolist(), pv.tolist(), pc.tolist()):
+            i = zpos.get(float(z))
+            if i is None:
+                continue
+            t2[i] += c
+            j = int(np.searchsorted(bounds, v, side="left"))
+            if j < len(cats):
+                c2[j][i] += c
+        np.testing.assert_array_equal(total, t2)
+        np.testing.assert_array_equal(counts, c2)

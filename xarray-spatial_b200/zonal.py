@@ -405,6 +405,31 @@ def stats(zones, values, zone_ids=None,
 TOTAL_COUNT = '_total_count'
 
 
+def _pivot_pairs(sel, cats, pz, pv, pc):
+    """(zone, value, count) pairs -> per-zone totals (float32, like the reference) and a
+    (len(cats), len(sel)) count matrix.  `cats` is sorted; zones outside `sel` are dropped.
+    zonal.py:719-727: a selected category also collects the unselected categories between it and
+    the previous selected one (the reference's `cat_start` only advances at selected categories);
+    with all categories selected this is the plain per-category count."""
+    total = np.zeros(len(sel), dtype=np.float32)
+    counts = np.zeros((len(cats), len(sel)), dtype=np.int64)
+    if len(sel) == 0 or len(pz) == 0:
+        return total, counts
+    sel_f = np.asarray(sel, dtype=np.float64)
+    order = np.argsort(sel_f, kind="stable")
+    pos = np.searchsorted(sel_f[order], pz.astype(np.float64), side="right") - 1   # last of equal ids
+    pos[pos < 0] = 0
+    hit = sel_f[order][pos] == pz
+    row = order[pos]
+    np.add.at(total, row[hit], pc[hit].astype(np.float32))      # unbuffered: pair order, like a loop
+    if len(cats):
+        bounds = np.asarray([float(c) for c in cats], dtype=np.float64)
+        col = np.searchsorted(bounds, pv, side="left")
+        keep = hit & (col < len(cats))
+        np.add.at(counts, (col[keep], row[keep]), pc[keep])
+    return total, counts
+
+
 def crosstab(zones, values, zone_ids=None, cat_ids=None, layer=None, agg="count", nodata_values=None, comm=None):
     """Cross-tabulated cell counts (or percentages) of the categories of a 2-D `values` raster
     per zone (zonal.py:922-1155, 2-D case): DataFrame with a `zone` column and one column per
@@ -442,22 +467,9 @@ def crosstab(zones, values, zone_ids=None, cat_ids=None, layer=None, agg="count"
         sel = unique_zones
     else:
         sel = np.array([z for z in zone_ids if z in unique_zones], dtype=unique_zones.dtype)
-    zpos = {float(z): i for i, z in enumerate(sel)}
     cats = sorted(cats)
-    table = {c: np.zeros(len(sel), dtype=np.int64) for c in cats}
-    total = np.zeros(len(sel), dtype=np.float32)
-    bounds = np.asarray([float(c) for c in cats], dtype=np.float64)
-    for z, v, c in zip(pz.tolist(), pv.tolist(), pc.tolist()):
-        i = zpos.get(float(z))
-        if i is None:
-            continue
-        total[i] += c
-        # zonal.py:719-727: a selected category also collects the unselected categories between it
-        # and the previous selected one (the reference's `cat_start` only advances at selected
-        # categories); with cat_ids=None this is the plain per-category count
-        j = int(np.searchsorted(bounds, v, side="left"))
-        if j < len(cats):
-            table[cats[j]][i] += c
+    total, counts = _pivot_pairs(sel, cats, pz, pv, pc)
+    table = {c: counts[j] for j, c in enumerate(cats)}
     d = {"zone": sel}
     if agg == "percentage":
         total[total == 0] = np.nan
