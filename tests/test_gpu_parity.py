@@ -648,6 +648,30 @@ def test_pitched_and_ragged_inputs(xb):
     assert_close_f32(host(xb.slope(agg)), o.slope(big, 30.0, -30.0, nthreads=8), what="negative cellsize_y")
 
 
+def test_ragged_widths_every_strip_operator(xb):
+    """Widths TMA cannot describe (W % 4 != 0) go through the cp.async ring with transposed,
+    coalesced 4-byte stores: every operator of the skeleton, single- and multi-output, f32 and f64."""
+    rng = np.random.default_rng(23)
+    for (h, w) in ((70, 131), (129, 257), (40, 1023), (33, 5)):
+        z = terrain(rng, h, w, nans=0.01)
+        agg = da(xb, dev(z))
+        assert_close_f32(host(xb.slope(agg)), o.slope(z, 30.0, 30.0, nthreads=4), what="slope %dx%d" % (h, w))
+        assert used_tma(xb) == 0
+        assert_aspect_close(host(xb.aspect(agg)), o.aspect(z, nthreads=4), what="aspect %dx%d" % (h, w))
+        ref_c = o.curvature(z, 30.0, nthreads=4)
+        assert_close_f32(host(xb.curvature(agg)), ref_c, atol=1e-6 * max(np.nanmax(np.abs(ref_c)), 1e-30),
+                         what="curvature %dx%d" % (h, w))
+        assert_close_f32(host(xb.hillshade(agg)), o.hillshade(z, nthreads=4), what="hillshade %dx%d" % (h, w))
+        assert_close_f32(host(xb.mean(agg)), o.focal_mean(z, nthreads=4), atol=0, what="mean %dx%d" % (h, w))
+        m64 = host(xb.mean(da(xb, dev(z.astype(np.float64)))))
+        assert m64.dtype == np.float64
+        np.testing.assert_allclose(m64, o.focal_mean(z.astype(np.float64), nthreads=4), rtol=1e-12, equal_nan=True)
+        suite = xb.surface_suite(agg)
+        for name in ("slope", "curvature", "hillshade"):
+            np.testing.assert_array_equal(host(suite[name]), host(getattr(xb, name)(agg)), err_msg="suite " + name)
+        np.testing.assert_array_equal(host(suite["aspect"]), host(xb.aspect(agg)))
+
+
 def test_integer_and_f64_inputs_are_cast_like_the_reference(xb):
     # tests/test_slope.py:70-79 parametrises over int32/int64/uint32/uint64/float32/float64
     base = np.random.default_rng(2841).integers(-100, 100, size=(10, 15))
