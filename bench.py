@@ -43,6 +43,11 @@ ALG_BYTES_PER_CELL = 8.0  # 4 B read + 4 B written per cell for each 3x3 float32
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons every 20 ms.  The process is started before the warm-up
+    steps (its start-up takes longer than a short timed region); `mark()` is called when the timed
+    region begins and `stop()` right after it ends, and only the rows printed in between are
+    reported.  If the timed region is shorter than two samples, the warm-up rows (same kernels,
+    same load) are included and `window` says so."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -51,12 +56,13 @@ class ClockSampler(object):
         self.rows = []
         self.proc = None
         self.gpu_index = gpu_index
+        self.i0 = 0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -66,18 +72,29 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def wait_first(self, timeout=2.0):
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        self.i0 = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        i1 = len(self.rows)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        rows, window = self.rows[self.i0:i1], "timed region"
+        if len(rows) < 2:
+            rows, window = self.rows[:max(i1, 1)], "warm-up + timed region (timed region shorter than two samples)"
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -91,7 +108,8 @@ class ClockSampler(object):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "window": window,
+                "reasons": sorted(reasons)}
 
 
 def measured_peak_gbs():
@@ -245,18 +263,20 @@ def run_gpu_arm(args):
     parity = None
     if rank == 0 and n_gpus == 1 and not args.skip_host:
         parity = run_parity_gate(xb, stripes, attrs)     # before any timing
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()           # before the warm-up: nvidia-smi needs ~0.1 s to print its first row
+        sampler.wait_first()
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
     assert lib.xrs_debug_last_used_tma() == 1, "TMA kernels were not selected"
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     t_begin = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     t_begin.record()
     for i in range(args.steps):
         step(ev[i])
