@@ -18,7 +18,7 @@
 namespace xrs {
 
 constexpr int kZhThreads = 256;
-constexpr int kZhLocalCap = 1024;       // per-CTA table slots (power of two)
+constexpr int kZhLocalCap = 1024;       // per-CTA table slots of the pair kernel (x2) and of float64 values
 constexpr int kZhUnroll = 4;            // rows per lane in flight
 constexpr int kZhSegRows = 256;         // rows per task
 constexpr long long kZhEmpty = (long long)0x8000000000000000ULL;
@@ -58,6 +58,41 @@ __device__ __forceinline__ void zh_atomic_max(double *addr, double v) {
         old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
         if (old == assumed) break;
     }
+}
+
+// float32 values keep their per-CTA min / max as order-preserving int32 keys, so that the table
+// update is one native ATOMS.MIN / ATOMS.MAX (shared memory has native atomics for 32-bit
+// integers only: float and every 64-bit type compile to compare-and-swap loops) and a slot takes
+// 36 bytes.  That buys 1408 slots per CTA inside the same 164 KB shared-memory carve-out as before
+// (3 CTAs / SM; a larger carve-out leaves too little L1 for the loads in flight -- 2048 slots
+// measured 20 % slower on coherent zones): a CTA that meets ~1000 distinct zones (scattered zone
+// ids, the worst case of SURVEY.md 8d) no longer fills its table and falls back to global atomics.
+__device__ __forceinline__ int zh_fkey(float f) {
+    const int b = __float_as_int(f);
+    return b ^ ((b >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float zh_funkey(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+template <typename VT> struct ZhMinMax { using type = double; };
+template <> struct ZhMinMax<float> { using type = int; };
+template <typename VT> struct ZhTable {
+    static constexpr int kCap = sizeof(VT) == 4 ? 1408 : kZhLocalCap;   // need not be a power of two
+    static constexpr size_t kBytes = (size_t)kCap * (8 + 8 + 8 + 2 * sizeof(typename ZhMinMax<VT>::type) + 4);
+};
+
+// find-or-insert in a per-CTA table of any size: start slot by multiply-shift range reduction
+__device__ __forceinline__ int zh_slot_local(long long *keys, int cap, long long key, int max_probe) {
+    unsigned s = __umulhi(zh_hash(key), (unsigned)cap);
+    for (int p = 0; p < max_probe; ++p) {
+        const long long k = keys[s];
+        if (k == key) return (int)s;
+        if (k == kZhEmpty) {
+            const long long prev = (long long)atomicCAS(reinterpret_cast<unsigned long long *>(&keys[s]),
+                                                        (unsigned long long)kZhEmpty, (unsigned long long)key);
+            if (prev == kZhEmpty || prev == key) return (int)s;
+        }
+        s = (s + 1 == (unsigned)cap) ? 0u : s + 1;
+    }
+    return -1;
 }
 
 // find-or-insert `key`; returns the slot or -1 when `max_probe` slots were all taken by others
@@ -173,12 +208,20 @@ template <typename T> __device__ __forceinline__ ZhQuad<T> zh_load(const T *p, i
 
 template <typename VT, typename ZT>
 __global__ void __launch_bounds__(kZhThreads, 3) zonal_hash_kernel(const __grid_constant__ ZhArgs a) {
-    __shared__ long long s_keys[kZhLocalCap];
-    __shared__ double s_s1[kZhLocalCap], s_s2[kZhLocalCap], s_mn[kZhLocalCap], s_mx[kZhLocalCap];
-    __shared__ unsigned s_cnt[kZhLocalCap];
-    for (int i = threadIdx.x; i < kZhLocalCap; i += blockDim.x) {
+    using MM = typename ZhMinMax<VT>::type;
+    constexpr int kCap = ZhTable<VT>::kCap;
+    extern __shared__ __align__(16) unsigned char zh_smem[];
+    long long *s_keys = reinterpret_cast<long long *>(zh_smem);
+    double *s_s1 = reinterpret_cast<double *>(s_keys + kCap);
+    double *s_s2 = s_s1 + kCap;
+    MM *s_mn = reinterpret_cast<MM *>(s_s2 + kCap);
+    MM *s_mx = s_mn + kCap;
+    unsigned *s_cnt = reinterpret_cast<unsigned *>(s_mx + kCap);
+    for (int i = threadIdx.x; i < kCap; i += blockDim.x) {
         s_keys[i] = kZhEmpty;
-        s_s1[i] = 0.0; s_s2[i] = 0.0; s_mn[i] = INFINITY; s_mx[i] = -INFINITY; s_cnt[i] = 0u;
+        s_s1[i] = 0.0; s_s2[i] = 0.0; s_cnt[i] = 0u;
+        if constexpr (sizeof(VT) == 4) { s_mn[i] = zh_fkey(INFINITY); s_mx[i] = zh_fkey(-INFINITY); }
+        else { s_mn[i] = INFINITY; s_mx[i] = -INFINITY; }
     }
     __syncthreads();
 
@@ -196,14 +239,19 @@ __global__ void __launch_bounds__(kZhThreads, 3) zonal_hash_kernel(const __grid_
     // merge (key, cnt, s1, s2, mn, mx) into the CTA table, spilling to the global table when the
     // CTA sees more distinct zones than its table holds
     auto merge = [&](long long key, unsigned cnt, double s1, double s2, double mn, double mx) {
-        int s = zh_slot(s_keys, kZhLocalCap, key, 48);
+        int s = zh_slot_local(s_keys, kCap, key, 48);
         if (s >= 0) {
             if (cnt) {
                 atomicAdd(&s_cnt[s], cnt);
                 atomicAdd(&s_s1[s], s1);
                 atomicAdd(&s_s2[s], s2);
-                zh_atomic_min(&s_mn[s], mn);
-                zh_atomic_max(&s_mx[s], mx);
+                if constexpr (sizeof(VT) == 4) {
+                    atomicMin(&s_mn[s], zh_fkey((float)mn));   // mn / mx came from float32 cells: exact
+                    atomicMax(&s_mx[s], zh_fkey((float)mx));
+                } else {
+                    zh_atomic_min(&s_mn[s], mn);
+                    zh_atomic_max(&s_mx[s], mx);
+                }
             }
         } else {
             s = zh_slot(a.keys, a.cap, key, a.cap);
@@ -320,7 +368,7 @@ __global__ void __launch_bounds__(kZhThreads, 3) zonal_hash_kernel(const __grid_
     }
     flush_all(have);
     __syncthreads();
-    for (int i = threadIdx.x; i < kZhLocalCap; i += blockDim.x) {
+    for (int i = threadIdx.x; i < kCap; i += blockDim.x) {
         const long long key = s_keys[i];
         if (key != kZhEmpty) {
             const int s = zh_slot(a.keys, a.cap, key, a.cap);
@@ -329,8 +377,13 @@ __global__ void __launch_bounds__(kZhThreads, 3) zonal_hash_kernel(const __grid_
             atomicAdd(&a.count[s], (unsigned long long)s_cnt[i]);
             atomicAdd(&a.s1[s], s_s1[i]);
             atomicAdd(&a.s2[s], s_s2[i]);
-            zh_atomic_min(&a.vmin[s], s_mn[i]);
-            zh_atomic_max(&a.vmax[s], s_mx[i]);
+            if constexpr (sizeof(VT) == 4) {
+                zh_atomic_min(&a.vmin[s], (double)zh_funkey(s_mn[i]));
+                zh_atomic_max(&a.vmax[s], (double)zh_funkey(s_mx[i]));
+            } else {
+                zh_atomic_min(&a.vmin[s], s_mn[i]);
+                zh_atomic_max(&a.vmax[s], s_mx[i]);
+            }
         }
     }
 }
@@ -432,14 +485,16 @@ __global__ void zonal_hash_init_kernel(long long *keys, unsigned long long *coun
 template <typename VT, typename ZT> static int launch_zh(const ZhArgs &a, cudaStream_t s) {
     const int64_t H = a.n / a.W;
     const int64_t n_tasks = ((a.W + 127) / 128) * ((H + kZhSegRows - 1) / kZhSegRows);
+    constexpr size_t smem = ZhTable<VT>::kBytes;
+    XRS_CUDA(cudaFuncSetAttribute(zonal_hash_kernel<VT, ZT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zonal_hash_kernel<VT, ZT>, kZhThreads, 0));
+    XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zonal_hash_kernel<VT, ZT>, kZhThreads, smem));
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)sm_count() * per_sm;
     const int64_t need = (n_tasks + kZhThreads / 32 - 1) / (kZhThreads / 32);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    zonal_hash_kernel<VT, ZT><<<(unsigned)grid, kZhThreads, 0, s>>>(a);
+    zonal_hash_kernel<VT, ZT><<<(unsigned)grid, kZhThreads, smem, s>>>(a);
     XRS_CUDA(cudaGetLastError());
     return XRS_OK;
 }
