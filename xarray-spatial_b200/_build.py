@@ -45,7 +45,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out.decode())
             raise RuntimeError("nvcc failed on %s" % src)
     if force or procs or not os.path.exists(SO):
-        cmd = [nvcc, "-shared", "-o", SO] + objs + ["-cudart", "static"]
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO] + objs + ["-cudart", "static"]
         subprocess.check_call(cmd)
     return SO
 
