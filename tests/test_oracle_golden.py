@@ -249,3 +249,131 @@ def test_geodesic_vs_reference(refout):
     np.testing.assert_allclose(o.geodesic(z, r["geodesic.lat2d"], r["geodesic.lon2d"], aspect=True),
                                r["geodesic.aspect_2d"], rtol=1e-6, atol=1e-4, equal_nan=True)
     assert (r["geodesic.aspect"] == -1).any() and np.isnan(r["geodesic.slope"][1:-1, 1:-1]).any()
+
+
+# ----------------------------------------------------------------- geodesic: the reference's own property tests
+# tests/test_geodesic_slope.py:76-199 and tests/test_geodesic_aspect.py:81-190 hold no tables, only
+# analytical expectations on small coarse grids (1 degree over 6 x 8 cells); the oracle must meet them.
+def _geo_grid(elev, la0, la1, lo0=10.0, lo1=11.0):
+    h, w = elev.shape
+    lat, lon = np.linspace(la0, la1, h), np.linspace(lo0, lo1, w)
+    return np.broadcast_to(lat[:, None], (h, w)).copy(), np.broadcast_to(lon[None, :], (h, w)).copy(), lat, lon
+
+
+def _tilted(axis, sign, h=6, w=8, grade=100.0):
+    ramp = np.linspace(0.0, 1.0, w if axis == "east" else h) * grade * sign
+    return (np.broadcast_to(500.0 + ramp[None, :], (h, w)) if axis == "east"
+            else np.broadcast_to(500.0 + ramp[:, None], (h, w))).copy()
+
+
+@pytest.mark.parametrize("lat_center", [0.0, 30.0, 60.0, -45.0])
+def test_geodesic_flat_surface_like_reference_tests(lat_center):
+    flat = np.full((6, 8), 500.0)
+    la, lo, _, _ = _geo_grid(flat, lat_center - 0.5, lat_center + 0.5)
+    s = o.geodesic(flat, la, lo)
+    assert np.isfinite(s[1:-1, 1:-1]).all()
+    np.testing.assert_allclose(s[1:-1, 1:-1], 0.0, atol=0.1)             # test_geodesic_slope.py:76-89
+    a = o.geodesic(flat, la, lo, aspect=True)
+    np.testing.assert_allclose(a[1:-1, 1:-1], -1.0, atol=1e-4)           # test_geodesic_aspect.py:81-87
+    for out in (s, a):                                                    # edges are NaN (:152-160 / :144-151)
+        assert np.isnan(out[0]).all() and np.isnan(out[-1]).all() and np.isnan(out[:, 0]).all() and np.isnan(out[:, -1]).all()
+
+
+def test_geodesic_tilted_surfaces_like_reference_tests():
+    expect = {("east", 1): 270.0, ("north", 1): 180.0, ("north", -1): 0.0, ("east", -1): 90.0}
+    for (axis, sign), asp in expect.items():
+        z = _tilted(axis, sign)
+        la, lo, _, _ = _geo_grid(z, 40.0, 41.0)
+        s = o.geodesic(z, la, lo)[1:-1, 1:-1]
+        assert np.isfinite(s).all() and (s > 0).all()                     # test_geodesic_slope.py:92-109
+        a = float(o.geodesic(z, la, lo, aspect=True)[2, 4])               # test_geodesic_aspect.py:89-131
+        d = abs(a - asp)
+        assert min(d, 360.0 - d) < 5.0, (axis, sign, a)
+    # latitude invariance (:112-137): the same grade per degree of longitude is ~2x steeper at 60N
+    z = _tilted("east", 1, grade=50.0)
+    s_eq = o.geodesic(z, *_geo_grid(z, -0.5, 0.5)[:2])[2, 4]
+    s_60 = o.geodesic(z, *_geo_grid(z, 59.5, 60.5)[:2])[2, 4]
+    assert s_eq > 0 and 1.5 < s_60 / s_eq < 2.5
+    # near the pole (:162-173) and feet vs metres (:179-199)
+    zp = _tilted("north", 1, h=6, w=6, grade=50.0)
+    sp = o.geodesic(zp, *_geo_grid(zp, 88.0, 89.0)[:2])[1:-1, 1:-1]
+    assert np.isfinite(sp).all() and (sp > 0).all()
+    zm = _tilted("east", 1)
+    la, lo, _, _ = _geo_grid(zm, 40.0, 41.0)
+    np.testing.assert_allclose(o.geodesic(zm, la, lo)[1:-1, 1:-1],
+                               o.geodesic(zm / 0.3048, la, lo, z_factor=0.3048)[1:-1, 1:-1], rtol=1e-4)
+    # NaN in the neighbourhood (:140-150)
+    zn = np.full((5, 5), 500.0)
+    zn[2, 2] = np.nan
+    sn = o.geodesic(zn, *_geo_grid(zn, 40.0, 41.0)[:2])
+    assert np.isnan(sn[2, 2]) and np.isnan(sn[1, 1]) and np.isnan(sn[1, 2])
+    # aspect range (:153-166)
+    zr = np.random.default_rng(42).uniform(100, 1000, size=(10, 10))
+    ar = o.geodesic(zr, *_geo_grid(zr, 40.0, 41.0)[:2], aspect=True)[1:-1, 1:-1]
+    d = ar[np.isfinite(ar) & (ar != -1.0)]
+    assert (d >= 0.0).all() and (d < 360.0).all()
+
+
+def _geodesic_folded(z, lat, lon, zf=1.0, aspect=False):
+    """NumPy statement of the regular-grid algebra of csrc/geodesic.cu (t = (N + h) cos lat,
+    Z = (b^2/a^2 N + h) sin lat, D = lon_k - lon_c; e = t_k sin D, p = t_k cos D - t_c, w = Z_k - Z_c,
+    n = cos(lat_c) w - sin(lat_c) p, u = cos(lat_c) p + sin(lat_c) w) -- checked here against the
+    oracle, which forms the same quantities through ECEF X, Y, Z like geodesic.py:60-118."""
+    a2, b2, inv2r = 6378137.0 ** 2, 6356752.314245 ** 2, 1.0 / (2.0 * 6370994.884953014)
+    h_, w_ = z.shape
+    la = np.radians(lat)
+    s, c = np.sin(la), np.cos(la)
+    n_ = a2 / np.sqrt(a2 * c * c + b2 * s * s)
+    m_ = b2 / a2 * n_
+    dl = np.radians(np.diff(lon))
+    sd, cd = np.sin(dl), np.cos(dl)
+    out = np.full((h_, w_), np.nan)
+    for y in range(1, h_ - 1):
+        for x in range(1, w_ - 1):
+            h9 = z[y - 1:y + 2, x - 1:x + 2] * zf
+            if np.isnan(h9).any():
+                continue
+            tc, zc = (n_[y] + h9[1, 1]) * c[y], (m_[y] + h9[1, 1]) * s[y]
+            es, ns, us = [], [], []
+            for dy in range(3):
+                for dx in range(3):
+                    if dy == 1 and dx == 1:
+                        continue
+                    r = y + dy - 1
+                    t, zz = (n_[r] + h9[dy, dx]) * c[r], (m_[r] + h9[dy, dx]) * s[r]
+                    q, e = (t, 0.0) if dx == 1 else ((t * cd[x - 1], -t * sd[x - 1]) if dx == 0 else (t * cd[x], t * sd[x]))
+                    p, w = q - tc, zz - zc
+                    n = c[y] * w - s[y] * p
+                    es.append(e), ns.append(n), us.append(c[y] * p + s[y] * w + (e * e + n * n) * inv2r)
+            e, n, u = np.array(es + [0.0]), np.array(ns + [0.0]), np.array(us + [0.0])
+            e, n, u = e - e.mean(), n - n.mean(), u - u.mean()
+            see, snn, sen, seu, snu = (e * e).sum(), (n * n).sum(), (e * n).sum(), (e * u).sum(), (n * u).sum()
+            det = see * snn - sen * sen
+            a_, b_ = (0.0, 0.0) if abs(det) < 1e-30 else ((seu * snn - snu * sen) / det, (snu * see - seu * sen) / det)
+            m2 = a_ * a_ + b_ * b_
+            if not aspect:
+                out[y, x] = np.degrees(np.arctan(np.sqrt(m2)))
+            elif m2 < 1e-14:
+                out[y, x] = -1.0
+            else:
+                ang = np.degrees(np.arctan2(-a_, -b_))
+                out[y, x] = ang + 360.0 if ang < 0 else ang
+    return out
+
+
+@pytest.mark.parametrize("lat0", [-0.5, 40.0, 59.5, 88.0])
+def test_geodesic_regular_grid_fold_equals_ecef_form(lat0):
+    """The algebraic fold used by the CUDA kernel on regular grids gives the oracle's (= the
+    reference's ECEF) numbers on coarse 1-degree grids too, where the longitude step is large."""
+    rng = np.random.default_rng(42)
+    cases = [np.full((6, 8), 500.0), _tilted("east", 1), _tilted("north", -1), rng.uniform(100, 1000, (10, 10))]
+    for z in cases:
+        la, lo, lat, lon = _geo_grid(z, lat0, lat0 + 1.0)
+        ref = o.geodesic(z, la, lo).astype(np.float64)
+        np.testing.assert_allclose(_geodesic_folded(z, lat, lon), ref, rtol=2e-6, atol=1e-7, equal_nan=True)
+        refa = o.geodesic(z, la, lo, aspect=True).astype(np.float64)
+        gota = _geodesic_folded(z, lat, lon, aspect=True)
+        np.testing.assert_array_equal(gota == -1, refa == -1)
+        m = ~np.isnan(refa) & (refa != -1)
+        d = np.abs(gota[m] - refa[m])
+        assert (np.minimum(d, 360 - d) < 1e-4).all()
