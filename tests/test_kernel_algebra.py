@@ -1,0 +1,155 @@
+"""CPU checks of the algebra the CUDA kernels use where it differs in FORM from the reference's
+(the GPU parity tests check the kernels themselves): NumPy statements of the kernel arithmetic
+against the pinned oracle, and the polynomial constants parsed out of the CUDA header."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle as o
+from helpers import terrain
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "xarray-spatial_b200", "csrc")
+
+
+def _atan_coeffs():
+    src = open(os.path.join(CSRC, "common.cuh")).read()
+    body = src[src.index("float atan_poly01(float z)"):]
+    body = body[:body.index("return p;")]
+    c = [float(x) for x in re.findall(r"(-?\d\.\d+e[+-]\d+)f \* k", body)]
+    assert len(c) == 8, c
+    return c                      # highest degree first
+
+
+def test_atan_polynomial_of_the_header_is_accurate_in_float32():
+    """atan(t)/t on [0, 1] as a degree-7 polynomial in t^2 (common.cuh): 2.5e-7 relative when
+    evaluated with float32 FMAs-free Horner steps, far inside the 1e-5 parity bar."""
+    c = np.array(_atan_coeffs(), dtype=np.float32)
+    t = np.linspace(0.0, 1.0, 200001, dtype=np.float32)
+    z = (t * t).astype(np.float32)
+    p = np.full_like(z, c[0])
+    for k in c[1:]:
+        p = (p * z + k).astype(np.float32)
+    got = (t * p).astype(np.float64)
+    ref = np.arctan(t.astype(np.float64))
+    rel = np.abs(got[1:] - ref[1:]) / ref[1:]
+    assert rel.max() < 4e-7, rel.max()
+
+
+def _compass(u, v, coeffs):
+    """NumPy statement of compass_deg (common.cuh): octant reduction + polynomial, float32."""
+    u, v = np.float32(u), np.float32(v)
+    au, av = abs(u), abs(v)
+    swap = au > av
+    mx, mn = (au, av) if swap else (av, au)
+    if mx == 0:
+        return np.float32(-1.0)
+    t = np.float32(mn / mx)
+    z = np.float32(t * t)
+    p = np.float32(coeffs[0] * np.float32(57.29578))
+    for k in coeffs[1:]:
+        p = np.float32(p * z + np.float32(k * np.float32(57.29578)))
+    base = np.float32(t * p)
+    sgn = (u < 0) != (v < 0)
+    sgn = (not sgn) if swap else sgn
+    sb = -base if sgn else base
+    if swap:
+        k0 = 90.0 if u > 0 else 270.0
+    else:
+        k0 = (360.0 if u < 0 else 0.0) if v > 0 else 180.0
+    return np.float32(np.float32(k0) + sb)
+
+
+def test_compass_fold_matches_the_reference_branches():
+    """aspect.py:74-88 maps atan2(dz_dy, -dz_dx) through three branches; the kernel evaluates
+    atan2(-X, Y) folded to [0, 360) per octant.  Same angles on a dense fan of directions, including
+    the axes and exact zeros."""
+    coeffs = [np.float32(x) for x in _atan_coeffs()]
+    rng = np.random.default_rng(0)
+    pts = [(x, y) for x in (-3.0, -1.0, -1e-20, 0.0, 1e-20, 1.0, 2.5) for y in (-2.0, -1.0, 0.0, 1e-20, 1.0, 7.0)]
+    pts += list(zip(rng.standard_normal(2000) * 10.0 ** rng.integers(-6, 6, 2000), rng.standard_normal(2000)))
+    for X, Y in pts:
+        if X == 0 and Y == 0:
+            assert _compass(-X, Y, coeffs) == -1
+            continue
+        th = np.degrees(np.arctan2(Y, -X))                     # dz_dy, -dz_dx up to the common factor 1/8
+        ref = 90.0 - th if th < 0 else (360.0 - th + 90.0 if th > 90.0 else 90.0 - th)
+        got = float(_compass(np.float32(0.0) - np.float32(X) if X == 0 else -X, Y, coeffs))
+        d = abs(got - ref)
+        assert min(d, 360.0 - d) <= 1e-5 * abs(ref) + 1e-4, (X, Y, got, ref)
+
+
+def _box_sat(z, kh, kw, w, th=32, tw=128, pad=16):
+    """NumPy statement of conv_box_kernel (conv.cu): per 128 x 32 tile a float64 summed-area table over
+    the tile + halo (out-of-raster cells count 0), out = w * (S[bot][right] - S[bot][left] - S[top][right]
+    + S[top][left]) + 0, NaN ring from coordinates, non-finite results recomputed tap by tap."""
+    H, W = z.shape
+    ry, rx = kh // 2, kw // 2
+    out = np.empty((H, W), np.float32)
+    zz = z.astype(np.float64)
+    for y0 in range(0, H, th):
+        for x0 in range(0, W, tw):
+            gy0, gx0 = y0 - ry - 1, x0 - pad
+            sh, sw = th + kh, 160
+            tile = np.zeros((sh, sw))
+            ys, xs = np.arange(gy0, gy0 + sh), np.arange(gx0, gx0 + sw)
+            my, mx = (ys >= 0) & (ys < H), (xs >= 0) & (xs < W)
+            tile[np.ix_(my, mx)] = zz[np.ix_(ys[my], xs[mx])]
+            with np.errstate(invalid="ignore"):
+                S = np.cumsum(np.cumsum(tile, axis=0), axis=1)
+            for oy in range(min(th, H - y0)):
+                for cx in range(min(tw, W - x0)):
+                    y, x = y0 + oy, x0 + cx
+                    if y < ry or y >= H - ry or x < rx or x >= W - rx:
+                        out[y, x] = np.nan
+                        continue
+                    left, right = pad + cx - rx - 1, pad + cx + rx
+                    with np.errstate(invalid="ignore"):
+                        res = w * ((S[oy + kh, right] - S[oy + kh, left]) - (S[oy, right] - S[oy, left])) + 0.0
+                    if not np.isfinite(res):
+                        acc = 0.0
+                        with np.errstate(invalid="ignore", over="ignore"):
+                            for v in zz[y - ry:y + ry + 1, x - rx:x + rx + 1].ravel():
+                                acc = acc + w * v
+                        res = acc
+                    with np.errstate(over="ignore"):
+                        out[y, x] = np.float32(res)
+    return out
+
+
+@pytest.mark.parametrize("kh,kw", [(5, 5), (9, 9), (3, 7), (25, 3)])
+def test_summed_area_box_convolution_equals_tap_order_sums(kh, kw):
+    rng = np.random.default_rng(kh * 31 + kw)
+    z = (terrain(rng, 70, 150) + 1e5).astype(np.float32)
+    dirty = z.copy()
+    dirty[10, 20] = np.nan
+    dirty[40, 100] = np.inf
+    for w in (1.0 / (kh * kw), -0.37):
+        for data in (z, dirty):
+            ref = o.convolve_2d(data, np.full((kh, kw), w), nthreads=4)
+            got = _box_sat(data, kh, kw, w)
+            np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
+            m = np.isfinite(ref)
+            np.testing.assert_array_equal(got[~m & ~np.isnan(ref)], ref[~m & ~np.isnan(ref)])   # +-inf cells
+            np.testing.assert_allclose(got[m], ref[m], rtol=1e-6, atol=1e-6 * np.abs(ref[m]).max())
+
+
+def test_focal_mean_division_by_count_is_correctly_rounded():
+    """div_count9 (surface_ops.cuh) replaces the float64 division s / n (n = 1..9 valid cells) by
+    q = s * (1/n), e = fma(-q, n, s), q + e * (1/n): with exact FMAs (emulated here with rationals)
+    that is the correctly rounded quotient, i.e. bit-identical to np.nanmean's division."""
+    from fractions import Fraction
+    rng = np.random.default_rng(9)
+    vals = np.concatenate([rng.standard_normal(4000) * 10.0 ** rng.integers(-8, 9, 4000),
+                           rng.integers(-40000, 40000, 2000).astype(np.float64), [0.0, 1.0, 4000.0 * 9, 1e-300, 1e300]])
+    bad = 0
+    for s in vals:
+        for n in range(1, 10):
+            r = 1.0 / n
+            q = s * r
+            e = float(Fraction(s) - Fraction(q) * n)            # fma(-q, n, s): one rounding
+            res = float(Fraction(e) * Fraction(r) + Fraction(q))  # fma(e, r, q): one rounding
+            bad += res != s / n
+    assert bad == 0
