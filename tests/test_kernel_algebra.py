@@ -153,3 +153,59 @@ def test_focal_mean_division_by_count_is_correctly_rounded():
             res = float(Fraction(e) * Fraction(r) + Fraction(q))  # fma(e, r, q): one rounding
             bad += res != s / n
     assert bad == 0
+
+
+@pytest.mark.parametrize("az,alt", [(225.0, 25.0), (0.0, 90.0), (90.0, 1.0), (315.0, 60.0)])
+def test_hillshade_closed_form_equals_the_trig_chain(az, alt):
+    """HillshadeOp (surface_ops.cuh) evaluates hillshade.py:20-35 -- np.gradient, atan, atan2, sin, cos --
+    as [sin(alt) + cos(alt) (cos A gy - sin A gx)] / sqrt(1 + gx^2 + gy^2), A = azimuth_rad - pi/2, in float32
+    with the doubled gradients gx2 = 2 gx, gy2 = 2 gy: no transcendental per cell.  Same numbers as the
+    oracle's trig chain (the float32 noise of either form is ~1e-7)."""
+    rng = np.random.default_rng(int(az + alt))
+    z = terrain(rng, 60, 90)
+    ref = o.hillshade(z, az, alt, nthreads=2).astype(np.float64)
+    azr = (360.0 - az) * np.pi / 180.0
+    altr = alt * np.pi / 180.0
+    a_ = azr - np.pi / 2.0
+    s0, cy, cx = np.float32(np.sin(altr)), np.float32(0.5 * np.cos(altr) * np.cos(a_)), np.float32(0.5 * np.cos(altr) * np.sin(a_))
+    gx2 = (z[2:, 1:-1] - z[:-2, 1:-1]).astype(np.float32)      # 2 * d/drow
+    gy2 = (z[1:-1, 2:] - z[1:-1, :-2]).astype(np.float32)      # 2 * d/dcol
+    q = (gx2 * gx2 + gy2 * gy2).astype(np.float32)
+    rinv = (1.0 / np.sqrt((np.float32(0.25) * q + np.float32(1.0)).astype(np.float64))).astype(np.float32)
+    num = (cy * gy2 + (-cx * gx2 + s0)).astype(np.float32)
+    got = (np.float32(0.5) * num * rinv + np.float32(0.5)).astype(np.float64)
+    np.testing.assert_allclose(got, ref[1:-1, 1:-1], rtol=1e-5, atol=1e-6)
+    assert np.isnan(ref[0]).all() and np.isnan(ref[:, 0]).all()
+
+
+def test_slope_sum_of_squares_form():
+    """SlopeOp: X = 8 csx dz_dx and Y = 8 csy dz_dy are exact in float64; the kernel forms
+    p = ky^2 ((X kx / ky)^2 + Y^2), rounds it to float32 once and takes atan(sqrt(p)) in float32."""
+    rng = np.random.default_rng(12)
+    z = terrain(rng, 50, 70)
+    for csx, csy in ((30.0, 30.0), (10.0, 25.0), (1.0, -1.0)):
+        ref = o.slope(z, csx, csy, nthreads=2).astype(np.float64)
+        zz = z.astype(np.float64)
+        # slope.py:64-71: a,b,c = row y+1; g,h,i = row y-1
+        X = (zz[2:, 2:] + 2 * zz[1:-1, 2:] + zz[:-2, 2:]) - (zz[2:, :-2] + 2 * zz[1:-1, :-2] + zz[:-2, :-2])
+        Y = (zz[:-2, :-2] + 2 * zz[:-2, 1:-1] + zz[:-2, 2:]) - (zz[2:, :-2] + 2 * zz[2:, 1:-1] + zz[2:, 2:])
+        kx, ky = 1.0 / (8.0 * csx), 1.0 / (8.0 * csy)
+        xs = X * (kx / ky)
+        p = (xs * xs + Y * Y).astype(np.float32) * np.float32(ky * ky)
+        got = np.degrees(np.arctan(np.sqrt(p.astype(np.float64)))) * (57.29578 / (180.0 / np.pi))
+        np.testing.assert_allclose(got, ref[1:-1, 1:-1], rtol=1e-5, atol=1e-6)
+
+
+def test_order_preserving_float_keys_of_the_zonal_table():
+    """zh_fkey / zh_funkey (zonal_hash.cu): int32 keys whose signed order is the float order, so the
+    per-CTA min / max are native integer atomics; the map is its own inverse."""
+    rng = np.random.default_rng(5)
+    f = np.concatenate([rng.standard_normal(5000).astype(np.float32) * np.float32(10.0) ** rng.integers(-30, 30, 5000),
+                        np.array([0.0, -0.0, np.inf, -np.inf, 1e-45, -1e-45, 3.4e38, -3.4e38], np.float32)]).astype(np.float32)
+    b = f.view(np.int32)
+    key = b ^ ((b >> 31) & np.int32(0x7fffffff))
+    back = (key ^ ((key >> 31) & np.int32(0x7fffffff))).view(np.float32)
+    np.testing.assert_array_equal(back.view(np.int32), b)
+    order = np.argsort(key, kind="stable")
+    assert (np.diff(f[order].astype(np.float64)) >= 0).all()
+    assert key[f == np.inf][0] == np.int32(0x7f800000) and (key[np.isfinite(f)] < np.int32(0x7f800000)).all()
