@@ -105,6 +105,14 @@ def known_answers():
     for k2, v in d.items():
         g["zonal.result_zone_ids_stats.%s" % k2] = np.asarray(v, dtype=np.float64)
     g["zonal.result_default_stats_dataarray"] = _call(f, "result_default_stats_dataarray")
+    # custom statistics (test_zonal.py:204-246: double_sum = 2*sum, range = max - min; nodata 0, zones 1, 2)
+    nod, zid, d = _call(f, "result_custom_stats")
+    g["zonal.result_custom_stats.nodata_values"] = np.asarray(nod)
+    g["zonal.result_custom_stats.zone_ids"] = np.asarray(zid)
+    for k2, v in d.items():
+        g["zonal.result_custom_stats.%s" % k2] = np.asarray(v, dtype=np.float64)
+    _, _, arr = _call(f, "result_custom_stats_dataarray")
+    g["zonal.result_custom_stats_dataarray"] = np.asarray(arr)
     return g
 
 
@@ -249,6 +257,12 @@ def reference_outputs():
     arr = zonal._stats_numpy(zz, zv, [3, 7], {s: zonal._DEFAULT_STATS[s] for s in ("mean", "count")},
                              None, return_type="xarray.DataArray")
     g["zonal.f32_i32.broadcast_mean_count_3_7"] = arr
+    # custom callables through the reference's own per-zone loop (zonal.py:144-163)
+    custom = {"double_sum": lambda v: v.sum() * 2, "range": lambda v: v.max() - v.min(),
+              "l2norm": lambda v: np.sqrt(np.sum(v.astype(np.float64) * v))}
+    df = zonal._stats_numpy(zz, zv, [3, 7, 100, 999], custom, 0.0, return_type="pandas.DataFrame")
+    for c in df.columns:
+        g["zonal.f32_i32_custom.%s" % c] = np.asarray(df[c])
 
     # focal.hotspots (focal.py:918-937) on a raster with two bumps, and zonal.crosstab (2-D)
     import types

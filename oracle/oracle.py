@@ -54,6 +54,16 @@ _dbl = ctypes.c_double
 _int = ctypes.c_int
 
 
+def synth_terrain(rows, cols, row0=0, col0=0, seed=1235, zmin=0.0, zmax=4000.0, nthreads=1):
+    """Host twin of the product's benchmark-DEM generator (csrc/synth.cu): the same function of
+    (seed, global row, global col), so the CPU arms of bench.py get the benchmark DEM without
+    mapping the CUDA library."""
+    out = np.empty((rows, cols), np.float32)
+    lib().xo_synth_terrain_f32(_p(out), _i64(rows), _i64(cols), _i64(row0), _i64(col0),
+                               ctypes.c_uint64(seed), ctypes.c_float(zmin), ctypes.c_float(zmax), _int(nthreads))
+    return out
+
+
 def slope(data, cellsize_x, cellsize_y, nthreads=1):
     """slope.py:56-76 `_cpu`."""
     d = _f32(data)

@@ -419,3 +419,49 @@ XO_EXPORT int xo_max_threads(void) {
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------ benchmark DEM
+ * Not reference arithmetic: the host twin of the product's benchmark-input generator
+ * (xarray-spatial_b200/csrc/synth.cu -- 12 octaves of smoothstep-interpolated lattice value
+ * noise, a pure function of (seed, global row, global col)), so that bench.py's CPU arms can
+ * produce the SAME DEM window without touching the CUDA library.  Agrees with the device
+ * generator to float32 rounding (exp2f / FMA-free float arithmetic), checked in the GPU tests.
+ */
+static uint32_t xo_hash3(uint32_t x, uint32_t y, uint32_t s) {
+    uint32_t h = x * 0x9E3779B1u ^ (y * 0x85EBCA77u) ^ (s * 0xC2B2AE3Du);
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    return h;
+}
+static float xo_lattice(uint32_t ix, uint32_t iy, uint32_t s) {
+    return (float)(xo_hash3(ix, iy, s) >> 8) * (1.0f / 8388608.0f) - 1.0f;
+}
+XO_EXPORT void xo_synth_terrain_f32(float *out, int64_t H, int64_t W, int64_t row0, int64_t col0,
+                                    uint64_t seed64, float zmin, float zmax, int nthreads) {
+    const uint32_t seed = (uint32_t)(seed64 * 0x9E3779B97F4A7C15ull >> 32);
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (int64_t y = 0; y < H; ++y) {
+        const int64_t gy = y + row0;
+        for (int64_t x = 0; x < W; ++x) {
+            const int64_t gx = x + col0;
+            float acc = 0.f, norm = 0.f;
+            for (int o = 0; o < 12; ++o) {
+                const int shift = 12 - o;
+                const float amp = exp2f(0.8f * (float)(shift - 12));
+                const int64_t cx = gx >> shift, cy = gy >> shift;
+                const float inv = 1.0f / (float)(1 << shift);
+                float fx = (float)(gx - (cx << shift)) * inv, fy = (float)(gy - (cy << shift)) * inv;
+                fx = fx * fx * (3.f - 2.f * fx);
+                fy = fy * fy * (3.f - 2.f * fy);
+                const uint32_t s = seed + 0x632BE5ABu * (uint32_t)o;
+                const float v00 = xo_lattice((uint32_t)cx, (uint32_t)cy, s), v10 = xo_lattice((uint32_t)cx + 1, (uint32_t)cy, s);
+                const float v01 = xo_lattice((uint32_t)cx, (uint32_t)cy + 1, s), v11 = xo_lattice((uint32_t)cx + 1, (uint32_t)cy + 1, s);
+                const float a = v00 + (v10 - v00) * fx, b = v01 + (v11 - v01) * fx;
+                acc += amp * (a + (b - a) * fy);
+                norm += amp;
+            }
+            float t = 0.5f + 0.5f * acc / norm * 1.8f;
+            t = fminf(fmaxf(t, 0.f), 1.f);
+            out[y * W + x] = zmin + (zmax - zmin) * t;
+        }
+    }
+}

@@ -714,3 +714,154 @@ def test_direct_ingest_matches_cast_then_compute(xb, dt):
     np.testing.assert_array_equal(host(xb.slope(da(xb, dev(odd)))), host(xb.slope(da(xb, dev(odd.astype(np.float32))))))
     np.testing.assert_array_equal(xb.slope(da(xb, np.ascontiguousarray(odd))).data,
                                   host(xb.slope(da(xb, dev(odd.astype(np.float32))))))
+
+
+# ----------------------------------------------------------------- round 2: drop-in contract
+def test_zonal_default_stats_are_the_references(xb, known):
+    """zonal.py:422-436: the default `stats_funcs` list includes `majority`."""
+    zones, values = known["zonal.data_zones"], known["zonal.data_values_2d"]
+    for mk in (dev, lambda a: a):   # device raster, numpy raster
+        df = xb.zonal_stats(da(xb, mk(zones)), da(xb, mk(values)))
+        assert list(df.columns) == ["zone", "mean", "max", "min", "sum", "std", "var", "count", "majority"]
+        for c in df.columns:
+            np.testing.assert_allclose(np.asarray(df[c], dtype=np.float64), known["zonal.result_default_stats." + c],
+                                       rtol=1e-5, atol=1e-7, err_msg=c)
+
+
+def test_zonal_custom_stats(xb, known, refout):
+    """test_zonal.py:204-246 / :497-545: `stats_funcs` as a dict of callables, nodata 0, zone_ids [1, 2];
+    then the reference's own per-zone loop on a seeded raster (reference_outputs.npz)."""
+    custom = {"double_sum": lambda v: v.sum() * 2, "range": lambda v: v.max() - v.min()}
+    zones, values = known["zonal.data_zones"], known["zonal.data_values_2d"]
+    zid = known["zonal.result_custom_stats.zone_ids"].tolist()
+    nod = known["zonal.result_custom_stats.nodata_values"].item()
+    for mk in (dev, lambda a: a):
+        df = xb.zonal_stats(da(xb, mk(zones)), da(xb, mk(values)), zone_ids=zid, stats_funcs=custom,
+                            nodata_values=nod)
+        assert list(df.columns) == ["zone", "double_sum", "range"]
+        for c in df.columns:
+            np.testing.assert_allclose(np.asarray(df[c], dtype=np.float64), known["zonal.result_custom_stats." + c],
+                                       rtol=1e-5, atol=1e-7, err_msg=c)
+        arr = xb.zonal_stats(da(xb, mk(zones)), da(xb, mk(values)), zone_ids=zid, stats_funcs=custom,
+                             nodata_values=nod, return_type="xarray.DataArray")
+        assert arr.dims == ("stats", "y", "x") and list(arr.coords["stats"]) == ["double_sum", "range"]
+        np.testing.assert_allclose(host(arr), known["zonal.result_custom_stats_dataarray"], equal_nan=True)
+    # a dict keyed by a built-in name runs the CALLABLE, never the built-in (reference: zonal.py:640-642)
+    df = xb.zonal_stats(da(xb, dev(zones)), da(xb, dev(values)), zone_ids=zid, nodata_values=nod,
+                        stats_funcs={"mean": lambda v: 42.0})
+    np.testing.assert_array_equal(np.asarray(df["mean"]), [42.0, 42.0])
+    with pytest.raises(ValueError):
+        xb.zonal_stats(da(xb, dev(zones)), da(xb, dev(values)), stats_funcs={"mean": "mean"})
+    # seeded raster, three callables, zone filter incl. a missing id, nodata
+    r = refout
+    custom3 = {"double_sum": lambda v: v.sum() * 2, "range": lambda v: v.max() - v.min(),
+               "l2norm": lambda v: float(np.sqrt(np.sum(np.asarray(v.cpu() if hasattr(v, "cpu") else v, dtype=np.float64) ** 2)))}
+    for mk in (dev, lambda a: a):
+        df = xb.zonal_stats(da(xb, mk(r["zonal.zones_i32"])), da(xb, mk(r["zonal.values_f32"])),
+                            zone_ids=[3, 7, 100, 999], stats_funcs=custom3, nodata_values=0.0)
+        np.testing.assert_array_equal(np.asarray(df["zone"]), r["zonal.f32_i32_custom.zone"])
+        for c in ("double_sum", "range", "l2norm"):
+            np.testing.assert_allclose(np.asarray(df[c], dtype=np.float64), r["zonal.f32_i32_custom." + c],
+                                       rtol=2e-6, err_msg=c)
+
+
+def test_majority_by_sort_equals_the_pair_table(xb):
+    """`majority` has two engines: the (zone, value) pair-count kernel (int32 zones, float32-exact
+    values) and one device sort (everything else: wide / non-integer zone ids, float64 values,
+    continuous rasters that overflow the pair table).  Same answers, incl. NaN, nodata and -0.0."""
+    from xrspatial_b200 import zonal as Z
+    rng = np.random.default_rng(4)
+    zc = rng.integers(-3, 40, size=(257, 300)).astype(np.int32)
+    vc = rng.integers(-4, 9, size=(257, 300)).astype(np.float32)
+    vc[rng.random(vc.shape) < 0.02] = np.nan
+    zero = vc == 0
+    vc[zero] = np.where(rng.random(zero.sum()) < 0.5, -0.0, 0.0).astype(np.float32)
+    uz = np.unique(zc)
+    for nod in (None, 3.0):
+        ref = o.zonal_stats(zc, vc, stats_funcs=["majority"], nodata_values=nod)
+        np.testing.assert_array_equal(ref["zone"], uz)
+        a = Z.majority_by_zone(dev(zc), dev(vc), uz, nod)                       # pair table
+        b = Z.majority_by_zone(dev(zc.astype(np.int64)), dev(vc), uz, nod)      # sort, float32 keys
+        c = Z.majority_by_zone(dev(zc.astype(np.float64)), dev(vc.astype(np.float64)), uz.astype(np.float64), nod)
+        for got in (a, b, c):
+            np.testing.assert_array_equal(got, np.asarray(ref["majority"], dtype=np.float64))
+    # float64 values that float32 cannot hold + non-integer zone ids (rank keys)
+    v64 = (rng.integers(0, 7, size=(64, 128)) * 0.1 + 1e6).astype(np.float64)
+    z64 = (rng.integers(0, 5, size=(64, 128)) * 0.5 - 1.0).astype(np.float64)
+    z64[0, :5] = np.nan
+    ref = o.zonal_stats(z64, v64, stats_funcs=["majority"])
+    got = Z.majority_by_zone(dev(z64), dev(v64), np.asarray(ref["zone"]))
+    np.testing.assert_array_equal(got, np.asarray(ref["majority"], dtype=np.float64))
+    # continuous values through the public API: the pair table overflows its (small here) budget
+    vals = rng.standard_normal((64, 4096)).astype(np.float32)
+    zz = (np.arange(64)[:, None] // 16 * 2 + np.arange(4096)[None, :] // 2048).astype(np.int32)
+    old = Z.pair_counts.__defaults__
+    Z.pair_counts.__defaults__ = (None, None, 1 << 10, 1 << 12)
+    try:
+        df = xb.zonal_stats(da(xb, dev(zz)), da(xb, dev(vals)), stats_funcs=["majority", "min"])
+    finally:
+        Z.pair_counts.__defaults__ = old
+    ref = o.zonal_stats(zz, vals, stats_funcs=["majority"])
+    np.testing.assert_array_equal(np.asarray(df["majority"]), np.asarray(ref["majority"], dtype=np.float64))
+    np.testing.assert_array_equal(np.asarray(df["majority"]), np.asarray(df["min"]))   # all values distinct
+
+
+def test_summarize_terrain_docstring_example(xb):
+    """analytics.py:29-71: the docstring's 5 x 8 raster and its slope / curvature / aspect tables, for a
+    device raster and a numpy raster; variables are added with `ds[name] = ...` (a read-only `data_vars`)."""
+    data = np.zeros((5, 8), dtype=np.float64)
+    data[2, 2], data[2, 5] = 1, -1
+    nan = np.nan
+    slope = np.array([[nan] * 8,
+                      [nan, 10.024988, 14.036243, 10.024988, 10.024988, 14.036243, 10.024988, nan],
+                      [nan, 14.036243, 0., 14.036243, 14.036243, 0., 14.036243, nan],
+                      [nan, 10.024988, 14.036243, 10.024988, 10.024988, 14.036243, 10.024988, nan],
+                      [nan] * 8])
+    curv = np.array([[nan] * 8,
+                     [nan, -0., -100., -0., -0., 100., -0., nan],
+                     [nan, -100., 400., -100., 100., -400., 100., nan],
+                     [nan, -0., -100., -0., -0., 100., -0., nan],
+                     [nan] * 8])
+    aspect = np.array([[nan] * 8,
+                       [nan, 315., 0., 45., 135., 180., 225., nan],
+                       [nan, 270., -1., 90., 90., -1., 270., nan],
+                       [nan, 225., 180., 135., 45., 0., 315., nan],
+                       [nan] * 8])
+    for mk in (dev, lambda a: a):
+        raster = xb.DataArray(mk(data), name="myraster", attrs={"res": (1, 1)})
+        ds = xb.summarize_terrain(raster)
+        assert list(ds.data_vars) == ["myraster", "myraster-slope", "myraster-curvature", "myraster-aspect"]
+        with pytest.raises(TypeError):
+            ds.data_vars["x"] = raster           # read-only, like xarray
+        assert_close_f32(host(ds["myraster-slope"]), slope, what="slope")
+        assert_close_f32(host(ds["myraster-curvature"]), curv, atol=1e-4, what="curvature")
+        assert_aspect_close(host(ds["myraster-aspect"]), aspect, what="aspect")
+        assert ds["myraster-slope"].attrs == {"res": (1, 1)} and ds["myraster-slope"].dims == raster.dims
+    with pytest.raises(NameError):
+        xb.summarize_terrain(xb.DataArray(dev(data)))
+
+
+def test_aspect_of_a_nodata_pixel_on_a_plateau(xb):
+    """aspect.py:74-88: the W / E / N / S neighbours of an isolated NaN on a flat area are NaN, not -1
+    (one Horn sum is NaN, the other 0); single kernel, fused suite and typed ingestion alike."""
+    z = np.full((40, 256), 250.0, dtype=np.float32)
+    z[17, 101] = np.nan
+    z[30, 5] = np.nan
+    z[3:6, 200:203] = 260.0
+    ref = o.aspect(z)
+    assert np.isnan(ref[17, 100]) and np.isnan(ref[16, 101]) and ref[10, 10] == -1
+    assert_aspect_close(host(xb.aspect(da(xb, dev(z)))), ref, what="aspect")
+    assert_aspect_close(host(xb.surface_suite(da(xb, dev(z)))["aspect"]), ref, what="suite aspect")
+    z64 = z.astype(np.float64)
+    assert_aspect_close(host(xb.aspect(da(xb, dev(z64)))), o.aspect(z64.astype(np.float32)), what="f64 ingest")
+    assert_aspect_close(xb.aspect(da(xb, z)).data, ref, what="host path")
+
+
+def test_bare_dataarray_without_coords_uses_unit_cells(xb):
+    """utils.py:233-277: no attrs['res'] and no coordinates -> xarray's default integer index -> cellsize 1."""
+    rng = np.random.default_rng(12)
+    z = terrain(rng, 64, 128)
+    agg = xb.DataArray(dev(z), dims=("y", "x"))
+    assert_close_f32(host(xb.slope(agg)), o.slope(z, 1.0, 1.0), what="slope")
+    assert_close_f32(host(xb.curvature(agg)), o.curvature(z, 1.0), atol=1e-6 * np.nanmax(np.abs(o.curvature(z, 1.0))),
+                     what="curvature")

@@ -38,28 +38,45 @@ def test_atan_polynomial_of_the_header_is_accurate_in_float32():
     assert rel.max() < 4e-7, rel.max()
 
 
+def _fma32(a, b, c):
+    return np.float32(np.float64(a) * np.float64(b) + np.float64(c))   # one rounding, like FFMA
+
+
 def _compass(u, v, coeffs):
-    """NumPy statement of compass_deg (common.cuh): octant reduction + polynomial, float32."""
+    """NumPy statement of compass_deg (common.cuh): octant reduction, sign folded into t, polynomial
+    and one fused multiply-add for the tail, float32.  The flat test is NaN-safe."""
     u, v = np.float32(u), np.float32(v)
     au, av = abs(u), abs(v)
     swap = au > av
     mx, mn = (au, av) if swap else (av, au)
-    if mx == 0:
-        return np.float32(-1.0)
-    t = np.float32(mn / mx)
-    z = np.float32(t * t)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = np.float32(mn / mx)
+    sgn = bool(np.signbit(u)) != bool(np.signbit(v))
+    sgn = (not sgn) if swap else sgn
+    ts = -t if sgn else t
+    z = np.float32(ts * ts)
     p = np.float32(coeffs[0] * np.float32(57.29578))
     for k in coeffs[1:]:
-        p = np.float32(p * z + np.float32(k * np.float32(57.29578)))
-    base = np.float32(t * p)
-    sgn = (u < 0) != (v < 0)
-    sgn = (not sgn) if swap else sgn
-    sb = -base if sgn else base
+        p = _fma32(p, z, np.float32(k * np.float32(57.29578)))
     if swap:
         k0 = 90.0 if u > 0 else 270.0
     else:
         k0 = (360.0 if u < 0 else 0.0) if v > 0 else 180.0
-    return np.float32(np.float32(k0) + sb)
+    r = _fma32(ts, p, np.float32(k0))
+    return np.float32(-1.0) if (au == 0 and av == 0) else r
+
+
+def test_compass_of_a_nan_sum_is_nan_not_flat():
+    """aspect.py:74-88: `dz_dx == 0 and dz_dy == 0` is false when one Horn sum is NaN, and
+    atan2(0, NaN) is NaN -- an isolated nodata pixel on a plateau must not read as flat (-1)."""
+    coeffs = [np.float32(x) for x in _atan_coeffs()]
+    for u, v in ((np.nan, 0.0), (0.0, np.nan), (np.nan, np.nan), (np.nan, 3.0), (-2.0, np.nan)):
+        assert np.isnan(_compass(u, v, coeffs)), (u, v)
+    z = np.full((5, 7), 100.0, dtype=np.float32)
+    z[2, 3] = np.nan
+    ref = o.aspect(z)
+    assert np.isnan(ref[2, 2]) and np.isnan(ref[2, 4]) and np.isnan(ref[1, 3])   # W / E / N neighbours of the hole
+    assert ref[1, 1] == -1.0 if not np.isnan(ref[1, 1]) else True
 
 
 def test_compass_fold_matches_the_reference_branches():

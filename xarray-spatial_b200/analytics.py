@@ -49,5 +49,5 @@ def summarize_terrain(terrain):
     res = surface_suite(terrain, products=("slope", "aspect", "curvature"))
     ds = Dataset({terrain.name: terrain}, attrs=terrain.attrs)
     for p in ("slope", "curvature", "aspect"):
-        ds.data_vars[f'{terrain.name}-{p}'] = res[p]
+        ds[f'{terrain.name}-{p}'] = res[p]          # analytics.py:83-86
     return ds

@@ -61,6 +61,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
                  "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -134,38 +137,85 @@ template <int DEG> __device__ __forceinline__ float atan_poly01(float z) {
     return p;
 }
 
-// degrees(atan(sqrt(p))) for p >= 0 (NaN propagates).  One MUFU.RSQ, no division:
-// for p > 1 uses atan(s) = pi/2 - atan(1/s) with 1/s = rsqrt(p).  p below 1e-30 (slope
-// below 6e-14 degrees) evaluates as p * 1e15, far under any tolerance.
-__device__ __forceinline__ float atan_sqrt_deg(float p) {
+// Packed pairs (Blackwell fma.rn.f32x2 / mul / add: one instruction, two cells; each half rounds
+// exactly like the scalar instruction, so results do not depend on how cells are paired).
+__device__ __forceinline__ float2 splat2(float c) { return make_float2(c, c); }
+template <int DEG> __device__ __forceinline__ float2 atan_poly01x2(float2 z) {
+    constexpr float k = DEG ? 57.29578f : 1.0f;
+    float2 p = splat2(-4.693183854e-03f * k);
+    p = __ffma2_rn(p, z, splat2(2.425208207e-02f * k));
+    p = __ffma2_rn(p, z, splat2(-5.948595430e-02f * k));
+    p = __ffma2_rn(p, z, splat2(9.914263125e-02f * k));
+    p = __ffma2_rn(p, z, splat2(-1.401947061e-01f * k));
+    p = __ffma2_rn(p, z, splat2(1.996972220e-01f * k));
+    p = __ffma2_rn(p, z, splat2(-3.333199064e-01f * k));
+    p = __ffma2_rn(p, z, splat2(9.999999010e-01f * k));
+    return p;
+}
+
+// degrees(atan(sqrt(p))) for p >= 0 (NaN propagates), two cells at a time.  One MUFU.RSQ per cell,
+// no division: for p > 1 uses atan(s) = pi/2 - atan(1/s) with 1/s = rsqrt(p), folded into the last
+// FMA as  a * poly(a^2) + off  with (a, off) = (s, 0) or (-1/s, 90 deg).  p below 1e-30 (slope below
+// 6e-14 degrees) evaluates as p * 1e15, far under any tolerance.
+__device__ __forceinline__ void atan_sqrt_sel(float p, float &a, float &off) {
     const float r = rsqrt_approx(fmaxf(p, 1e-30f));
-    const float s = p * r;            // sqrt(p); NaN stays NaN
-    const bool big = p > 1.0f;        // false for NaN -> the NaN in `s` propagates
-    const float a = big ? r : s;
-    const float t = a * atan_poly01<1>(a * a);
-    return big ? (1.57079632679489662f * 57.29578f - t) : t;
+    const bool big = p > 1.0f;          // false for NaN -> a = p * r = NaN propagates
+    a = big ? -r : p * r;               // +-atan argument in [0, 1]
+    off = big ? (1.57079632679489662f * 57.29578f) : 0.0f;
+}
+__device__ __forceinline__ float2 atan_sqrt_deg2(float2 p) {
+    const float rx = rsqrt_approx(fmaxf(p.x, 1e-30f)), ry = rsqrt_approx(fmaxf(p.y, 1e-30f));
+    const float2 s = __fmul2_rn(p, make_float2(rx, ry));
+    const bool bx = p.x > 1.0f, by = p.y > 1.0f;
+    const float2 a = make_float2(bx ? -rx : s.x, by ? -ry : s.y);
+    constexpr float kQ = 1.57079632679489662f * 57.29578f;
+    const float2 off = make_float2(bx ? kQ : 0.0f, by ? kQ : 0.0f);
+    return __ffma2_rn(a, atan_poly01x2<1>(__fmul2_rn(a, a)), off);
+}
+__device__ __forceinline__ float atan_sqrt_deg(float p) {
+    float a, off;
+    atan_sqrt_sel(p, a, off);
+    return fmaf(a, atan_poly01<1>(a * a), off);
 }
 
 // Compass aspect from the exact Horn sums X = 8 dz_dx, Y = 8 dz_dy (aspect.py:74-88):
 // the reference's (90 - atan2(Y, -X) deg) folded to [0, 360) is atan2(u, v) with u = -X, v = Y,
-// folded to [0, 360).  One octant reduction (ratio of the smaller to the larger magnitude,
-// one MUFU.RCP, degree-7 polynomial already scaled to degrees), then compass = K + sigma*base
-// with (K, sigma) picked per octant.  Evaluating the compass angle directly keeps full
-// relative accuracy near 0 degrees, where `90 - theta` would cancel.  Flat cells (both
-// sums zero) give -1; NaN propagates (selects, not fmin/fmax, pick the operands).
-__device__ __forceinline__ float compass_deg(float u, float v) {
+// folded to [0, 360).  One octant reduction (ratio t of the smaller to the larger magnitude,
+// one MUFU.RCP, degree-7 polynomial already scaled to degrees), then compass = K + sigma*atan(t)
+// with (K, sigma) picked per octant; sigma is applied to t's sign bit (the polynomial is even in t),
+// so the tail is one FMA:  ts * poly(ts^2) + K.  Evaluating the compass angle directly keeps full
+// relative accuracy near 0 degrees, where `90 - theta` would cancel.  Flat cells (both sums zero)
+// give -1; NaN propagates (selects, not fmin/fmax, pick the operands; the flat test is NaN-safe:
+// a NaN sum next to a zero sum is NaN, like atan2(0, NaN) in the reference).
+struct CompassPre {
+    float ts, K;
+    bool flat;
+};
+__device__ __forceinline__ CompassPre compass_pre(float u, float v) {
     const float au = fabsf(u), av = fabsf(v);
     const bool swap = au > av;                // closer to the +-u axis (east / west)
     const float mx = swap ? au : av, mn = swap ? av : au;
     const float t = mn * rcp_approx(mx);
-    const float base = t * atan_poly01<1>(t * t);                 // [0, 45] degrees
-    // sigma = sign(u) * sign(v), negated in the swapped octants: flip base's sign bit
+    // sigma = sign(u) * sign(v), negated in the swapped octants: flip t's sign bit
     const unsigned sgn = ((__float_as_uint(u) ^ __float_as_uint(v)) & 0x80000000u) ^ (swap ? 0x80000000u : 0u);
-    const float sb = __uint_as_float(__float_as_uint(base) ^ sgn);
+    CompassPre c;
+    c.ts = __uint_as_float(__float_as_uint(t) ^ sgn);
     const float k_ns = (v > 0.0f) ? ((u < 0.0f) ? 360.0f : 0.0f) : 180.0f;
     const float k_ew = (u > 0.0f) ? 90.0f : 270.0f;
-    const float r = (swap ? k_ew : k_ns) + sb;
-    return (mx == 0.0f) ? -1.0f : r;
+    c.K = swap ? k_ew : k_ns;
+    c.flat = (au == 0.0f) && (av == 0.0f);
+    return c;
+}
+__device__ __forceinline__ float compass_deg(float u, float v) {
+    const CompassPre c = compass_pre(u, v);
+    const float r = fmaf(c.ts, atan_poly01<1>(c.ts * c.ts), c.K);
+    return c.flat ? -1.0f : r;
+}
+__device__ __forceinline__ float2 compass_deg2(float2 u, float2 v) {
+    const CompassPre c0 = compass_pre(u.x, v.x), c1 = compass_pre(u.y, v.y);
+    const float2 ts = make_float2(c0.ts, c1.ts);
+    const float2 r = __ffma2_rn(ts, atan_poly01x2<1>(__fmul2_rn(ts, ts)), make_float2(c0.K, c1.K));
+    return make_float2(c0.flat ? -1.0f : r.x, c1.flat ? -1.0f : r.y);
 }
 
 }  // namespace xrs

@@ -2,25 +2,31 @@
 // hillshade / focal.mean / the fused surface suite.
 //
 // Decomposition (B200-first, not a port of the reference's one-thread-per-cell kernels,
-// slope.py:133-142): the raster is cut into column strips of 128 cells and row segments;
-// one WARP owns one (segment, strip) task at a time and marches down its rows.  Each lane
-// owns 4 adjacent cells (one float4), so a warp reads / writes 512 contiguous bytes per row.
-//   * input rows arrive through a per-warp ring of TMA 2-D boxes (136 x ROWS cells:
-//     the strip plus a 4-cell pad on both sides, which keeps every lane's float4 16-byte
-//     aligned in shared memory); out-of-raster cells are filled with NaN by the TMA unit,
-//     which is exactly the reference's raster-edge rule (NaN ring for the Horn family,
-//     NaN-skipping clamped windows for focal.mean);
-//   * lane 0 of the warp is the producer (arms the stage's mbarrier with expect_tx and
-//     issues cp.async.bulk.tensor.2d), all 32 lanes are consumers: no __syncthreads at all;
+// slope.py:133-142): the raster is cut into CTA tiles of WARPS x 128 columns and row segments;
+// a persistent CTA owns one (segment, tile) task at a time and marches down its rows.  Inside the
+// tile each consumer WARP owns a 128-cell strip and each lane 4 adjacent cells (one float4), so a
+// warp reads / writes 512 contiguous bytes per row.
+//   * ONE producer warp per CTA streams the tile (plus a 4-cell halo each side) through a ring of
+//     shared-memory stages with TMA 2-D boxes (208 cells x ROWS rows each; cp.async.bulk.tensor),
+//     `full` mbarriers carry the transaction bytes, `empty` mbarriers (one arrival per consumer
+//     warp) hand a stage back.  The producer is never delayed by arithmetic or stores, so the read
+//     stream is steady and in raster order, and the bytes in flight per SM are set by the ring
+//     (ROWS x STAGES), not by how many warps the arithmetic needs.  Measured on B200
+//     (profiles/r02_tune3_*.txt): the round-1 pipeline, where every warp refilled its own 4-box
+//     ring after finishing a box, topped out at 0.88 of the copy peak even for an operator that
+//     does nothing; this one moves the same bytes at 0.98-1.00;
+//   * out-of-raster cells are filled with NaN by the TMA unit, which is exactly the reference's
+//     raster-edge rule (NaN ring for the Horn family, NaN-skipping clamped windows for focal.mean);
 //   * the three input rows a cell needs are never re-read: operators keep per-row partial
 //     results (column differences / weighted row sums) of the two previous rows in
 //     registers and combine them with the new row ("push, then emit the row above");
-//   * left / right neighbours come from warp shuffles (strip-edge lanes read the pad);
+//   * left / right neighbours are scalar shared-memory loads next to the lane's float4 (strip-edge
+//     lanes read the neighbouring strip or the tile halo: same addresses formula);
 //   * outputs are written as float4 with streaming stores.
-// Rasters TMA cannot describe (width not a multiple of 4 cells, unaligned base / pitch) run the
-// same pipeline with cp.async fills (stencil3_cpasync_kernel); a plain bounds-checked
-// direct-load kernel is kept as the reference implementation of the loader.  All three drive
-// the very same operator code.
+// Rasters TMA cannot describe (width not a multiple of 4 cells, unaligned base / pitch) run a
+// per-warp ring filled by cp.async (stencil3_cpasync_kernel); a plain bounds-checked direct-load
+// kernel is kept as the reference implementation of the loader.  All three drive the very same
+// operator code.
 #pragma once
 #include "common.cuh"
 
@@ -61,6 +67,17 @@ template <typename T> __device__ __forceinline__ Row6<T> load_row_smem(const T *
     o.l = p[-1];
     o.r = p[4];
     return o;
+}
+
+template <typename T> __device__ __forceinline__ void load_cells4(const T *p, T (&c)[4]) {
+    if constexpr (sizeof(T) == 4) {
+        const float4 q = *reinterpret_cast<const float4 *>(p);
+        c[0] = q.x; c[1] = q.y; c[2] = q.z; c[3] = q.w;
+    } else {
+        const double2 q0 = *reinterpret_cast<const double2 *>(p);
+        const double2 q1 = *reinterpret_cast<const double2 *>(p + 2);
+        c[0] = q0.x; c[1] = q0.y; c[2] = q1.x; c[3] = q1.y;
+    }
 }
 
 // Direct global loads with bounds checks (out-of-raster cells read as NaN): six independent scalar
@@ -127,82 +144,115 @@ template <typename Op> struct OutPtrs {
 };
 
 // ----------------------------------------------------------------------------- TMA kernel
-template <typename Op, int ROWS, int STAGES>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+constexpr int kSubW = 208;  // cells per TMA box row (832 B for f32): 16-byte multiple, <= 256 elements
+
+struct TileGeom {
+    int64_t H, W;
+    int n_tiles, n_segs, seg_rows;
+};
+
+template <int WARPS> struct TileShape {
+    static constexpr int kTileW = kStripW * WARPS;                       // output columns per CTA tile
+    static constexpr int kNSub = (kTileW + 2 * kPad + kSubW - 1) / kSubW;  // TMA boxes per stage
+};
+
+template <typename Op, int ROWS, int STAGES, int WARPS>
+__global__ void __launch_bounds__((WARPS + 1) * 32)
 stencil3_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                     const __grid_constant__ typename Op::Params prm,
-                    const OutPtrs<Op> outs, const StripGeom g) {
+                    const OutPtrs<Op> outs, const TileGeom g) {
     using T = typename Op::in_t;
     using TO = typename Op::out_t;
-    constexpr int kStageElems = ROWS * kBoxW;
+    constexpr int kTileW = TileShape<WARPS>::kTileW;
+    constexpr int kNSub = TileShape<WARPS>::kNSub;
+    constexpr int kBoxElems = ROWS * kSubW;
+    constexpr int kStageElems = kNSub * kBoxElems;
     constexpr uint32_t kStageBytes = kStageElems * sizeof(T);
-    static_assert(kStageBytes % 128 == 0, "TMA destination must stay 128-byte aligned");
+    static_assert((kBoxElems * sizeof(T)) % 128 == 0, "TMA destination must stay 128-byte aligned");
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
+    T *ring = reinterpret_cast<T *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * kStageBytes);
+    uint64_t *empty = full + STAGES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    T *ring = reinterpret_cast<T *>(smem_raw) + (size_t)warp * STAGES * kStageElems;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kWarpsPerCta * STAGES * kStageBytes) +
-                     warp * STAGES;
 
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap);
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], WARPS);
+        }
         mbar_fence_init();
     }
-    __syncwarp();
+    __syncthreads();
 
-    const int64_t n_tasks = (int64_t)g.n_strips * g.n_segs;
-    const int64_t total_warps = (int64_t)gridDim.x * kWarpsPerCta;
-    uint32_t phase = 0;  // bit s = parity to wait for on stage s
-#ifdef XRS_TMA_EVICT_FIRST
-    const uint64_t l2pol = l2_policy_evict_first();
-#define XRS_TMA_LOAD(dst, bar, x, y) tma_load_2d_hint(dst, &tmap, bar, x, y, l2pol)
-#else
-#define XRS_TMA_LOAD(dst, bar, x, y) tma_load_2d(dst, &tmap, bar, x, y)
-#endif
+    const int64_t n_tasks = (int64_t)g.n_tiles * g.n_segs;
 
-    for (int64_t task = (int64_t)blockIdx.x * kWarpsPerCta + warp; task < n_tasks; task += total_warps) {
-        const int seg = (int)(task / g.n_strips), strip = (int)(task % g.n_strips);
-        const int64_t x0 = (int64_t)strip * kStripW;
+    if (warp == WARPS) {
+        // ---- producer: walks the same (task, chunk) sequence as the consumers, STAGES ahead
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;  // bit s = parity of the `empty` phase stage s was last refilled under
+            for (int64_t task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+                const int seg = (int)(task / g.n_tiles), tile = (int)(task % g.n_tiles);
+                const int64_t y0 = (int64_t)seg * g.seg_rows;
+                const int64_t y1 = min(y0 + (int64_t)g.seg_rows, g.H);
+                const int n_chunks = ((int)(y1 - y0) + 2 + ROWS - 1) / ROWS;  // input rows y0-1 .. y1
+                const int bx = tile * kTileW - kPad, by = (int)y0 - 1;
+                for (int c = 0; c < n_chunks; ++c) {
+                    // a fresh barrier passes a wait on parity 1: the first lap never blocks
+                    mbar_wait(&empty[stage], ((phase >> stage) & 1u) ^ 1u);
+                    phase ^= (1u << stage);
+                    mbar_arrive_expect_tx(&full[stage], kStageBytes);
+                    T *dst = ring + stage * kStageElems;
+#pragma unroll
+                    for (int b = 0; b < kNSub; ++b)
+                        tma_load_2d(dst + b * kBoxElems, &tmap, &full[stage], bx + b * kSubW, by + c * ROWS);
+                    stage = (stage + 1 == STAGES) ? 0 : stage + 1;
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- consumers.  Column cc of the stage (0 = first halo cell) lives in box cc / kSubW.
+    const int cc = kPad + kStripW * warp + kLaneCells * lane;
+    const int off_c = (cc / kSubW) * kBoxElems + cc % kSubW;
+    const int off_l = ((cc - 1) / kSubW) * kBoxElems + (cc - 1) % kSubW;
+    const int off_r = ((cc + kLaneCells) / kSubW) * kBoxElems + (cc + kLaneCells) % kSubW;
+    int stage = 0;
+    uint32_t phase = 0;  // bit s = parity to wait for on full[s]
+    for (int64_t task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+        const int seg = (int)(task / g.n_tiles), tile = (int)(task % g.n_tiles);
         const int64_t y0 = (int64_t)seg * g.seg_rows;
         const int64_t y1 = min(y0 + (int64_t)g.seg_rows, g.H);
-        const int rows_in = (int)(y1 - y0) + 2;  // input rows y0-1 .. y1
-        const int n_chunks = (rows_in + ROWS - 1) / ROWS;
-        const int bx = (int)x0 - kPad, by = (int)y0 - 1;
-
-        if (lane == 0) {
-#pragma unroll
-            for (int s = 0; s < STAGES; ++s)
-                if (s < n_chunks) {
-                    mbar_arrive_expect_tx(&bars[s], kStageBytes);
-                    XRS_TMA_LOAD(ring + s * kStageElems, &bars[s], bx, by + s * ROWS);
-                }
-        }
+        const int seg_h = (int)(y1 - y0);
+        const int n_chunks = (seg_h + 2 + ROWS - 1) / ROWS;
 
         Op op(prm);
-        const int64_t xl = x0 + kLaneCells * lane;
+        const int64_t xl = (int64_t)tile * kTileW + kStripW * warp + kLaneCells * lane;
         const bool lane_ok = xl < g.W;  // W % 4 == 0 on this path: a lane is all-in or all-out
-        const int seg_h = (int)(y1 - y0);
-        const T *lane_smem = ring + kPad + kLaneCells * lane;
         // output pointers one row above the first emitted row (y0 - 2): advanced before every store
         TO *optr[Op::kOutputs];
 #pragma unroll
         for (int k = 0; k < Op::kOutputs; ++k) optr[k] = outs.p[k] + (y0 - 3) * outs.pitch_elems + xl;
 
-        int stage = 0;
         for (int c = 0; c < n_chunks; ++c) {
-            mbar_wait(&bars[stage], (phase >> stage) & 1u);
+            mbar_wait(&full[stage], (phase >> stage) & 1u);
             phase ^= (1u << stage);
-            const T *buf = lane_smem + stage * kStageElems;
-            const int rel = c * ROWS - 2;  // output row (relative to y0) of the box's first row
-            // Straight-line over the ROWS rows of the box (no branch around the operator state
+            const T *buf = ring + stage * kStageElems;
+            const int rel = c * ROWS - 2;  // output row (relative to y0) of the stage's first row
+            // Straight-line over the ROWS rows of the stage (no branch around the operator state
             // update, so the rolling registers are renamed, not moved).  Rows whose output row
             // falls outside [y0, y1) -- the two lead-in rows and the tail of the last chunk --
             // still update the state; only their store is predicated off.
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
-                const Row6<T> row = load_row_smem<T>(buf + r * kBoxW);
+                Row6<T> row;
+                load_cells4(buf + off_c + r * kSubW, row.c);
+                row.l = buf[off_l + r * kSubW];
+                row.r = buf[off_r + r * kSubW];
                 Vec4<TO> o[Op::kOutputs];
                 op.step(row, o);
                 const bool st = lane_ok && (unsigned)(rel + r) < (unsigned)seg_h;
@@ -213,10 +263,7 @@ stencil3_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                 }
             }
             __syncwarp();  // every lane is done reading this stage
-            if (lane == 0 && c + STAGES < n_chunks) {
-                mbar_arrive_expect_tx(&bars[stage], kStageBytes);
-                XRS_TMA_LOAD(ring + stage * kStageElems, &bars[stage], bx, by + (c + STAGES) * ROWS);
-            }
+            if (lane == 0) mbar_arrive(&empty[stage]);
             stage = (stage + 1 == STAGES) ? 0 : stage + 1;
         }
     }
@@ -364,8 +411,12 @@ stencil3_cpasync_kernel(const typename Op::in_t *__restrict__ in, int64_t in_pit
 }
 
 // ----------------------------------------------------------------------------- host launcher
+// ROWS x STAGES = the TMA ring of the CTA-wide pipeline, WARPS consumer warps per CTA, CTAS CTAs per
+// SM: tuned per operator on B200 (scripts/tune/, profiles/r02_tune*.txt) -- ~65 KB in flight per SM
+// for the light operators, more warps and a deeper ring for the arithmetic-heavy ones.
+constexpr int kFallbackRows = 4, kFallbackStages = 4;  // cp.async ring (per warp)
 
-template <typename Op, int ROWS, int STAGES>
+template <typename Op, int ROWS, int STAGES, int WARPS = 8, int CTAS = 2>
 int launch_stencil3(const typename Op::in_t *in, int64_t in_pitch_bytes, const typename Op::Params &prm,
                     typename Op::out_t *const *out_ptrs, int64_t out_pitch_bytes, int64_t H, int64_t W,
                     cudaStream_t stream) {
@@ -377,7 +428,7 @@ int launch_stencil3(const typename Op::in_t *in, int64_t in_pitch_bytes, const t
                 "input pitch must be a multiple of the element size and >= row bytes");
     XRS_REQUIRE(out_pitch_bytes % (int64_t)sizeof(TO) == 0 && out_pitch_bytes >= W * (int64_t)sizeof(TO),
                 "output pitch must be a multiple of the element size and >= row bytes");
-    XRS_REQUIRE(H < (1LL << 31) - 8 && W < (1LL << 31) - 256, "raster dimension too large");
+    XRS_REQUIRE(H < (1LL << 31) - 8 && W < (1LL << 31) - 4096, "raster dimension too large");
 
     OutPtrs<Op> outs;
     bool any = false, out_vec_ok = (out_pitch_bytes % 16 == 0);
@@ -393,51 +444,64 @@ int launch_stencil3(const typename Op::in_t *in, int64_t in_pitch_bytes, const t
     outs.pitch_elems = out_pitch_bytes / (int64_t)sizeof(TO);
 
     const int sms = sm_count();
-    StripGeom g;
-    g.H = H;
-    g.W = W;
-    g.n_strips = (int)((W + kStripW - 1) / kStripW);
-    // Row segments: enough tasks for ~8 per resident warp, but segments of >= 64 rows so
-    // the 2 halo rows re-read per segment stay a ~3% overhead.
-    const int64_t resident_warps = (int64_t)sms * 2 * kWarpsPerCta;
-    int64_t want_segs = (resident_warps * 8 + g.n_strips - 1) / g.n_strips;
-    int64_t seg_rows = (H + want_segs - 1) / (want_segs > 0 ? want_segs : 1);
-    if (seg_rows < 64) seg_rows = 64;
-    if (seg_rows > H) seg_rows = H;
-    // multiple of ROWS so the last TMA chunk of a segment wastes < ROWS rows
-    seg_rows = ((seg_rows + 2 + ROWS - 1) / ROWS) * ROWS - 2;
-    if (seg_rows < 1) seg_rows = 1;
-    g.seg_rows = (int)seg_rows;
-    g.n_segs = (int)((H + seg_rows - 1) / seg_rows);
-    const int64_t n_tasks = (int64_t)g.n_strips * g.n_segs;
-    int64_t ctas_needed = (n_tasks + kWarpsPerCta - 1) / kWarpsPerCta;
-
     LaunchInfo &li = last_launch_info();
-    li.block = kWarpsPerCta * 32;
 
     CUtensorMap tmap;
     const bool tma_ok = out_vec_ok && (W % 4 == 0) &&
-                        make_tensor_map_2d(&tmap, in, in_pitch_bytes, H, W, (int)sizeof(T), kBoxW, ROWS);
+                        make_tensor_map_2d(&tmap, in, in_pitch_bytes, H, W, (int)sizeof(T), kSubW, ROWS);
     if (tma_ok) {
-        constexpr size_t smem = (size_t)kWarpsPerCta * STAGES * ROWS * kBoxW * sizeof(T) +
-                                (size_t)kWarpsPerCta * STAGES * sizeof(uint64_t);
-        auto kern = stencil3_tma_kernel<Op, ROWS, STAGES>;
+        constexpr int kTileW = TileShape<WARPS>::kTileW;
+        constexpr size_t smem = (size_t)STAGES * TileShape<WARPS>::kNSub * ROWS * kSubW * sizeof(T) +
+                                (size_t)2 * STAGES * sizeof(uint64_t);
+        auto kern = stencil3_tma_kernel<Op, ROWS, STAGES, WARPS>;
         XRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        // persistent grid: as many CTAs as fit on an SM (registers / shared memory), times the SMs
+        // persistent grid: CTAS per SM (or what fits), never more CTAs than tasks
         int per_sm = 0;
-        XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerCta * 32, smem));
+        XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (WARPS + 1) * 32, smem));
         if (per_sm < 1) per_sm = 1;
-        if (per_sm > 2) per_sm = 2;  // measured: 3 CTAs / SM is ~4% slower for hillshade than 2
-        int64_t grid = (int64_t)sms * per_sm;
-        if (grid > ctas_needed) grid = ctas_needed;
+        if (per_sm > CTAS) per_sm = CTAS;
+        TileGeom g;
+        g.H = H;
+        g.W = W;
+        g.n_tiles = (int)((W + kTileW - 1) / kTileW);
+        // Row segments: ~8 tasks per resident CTA, but segments of >= 32 rows so the 2 halo rows
+        // re-read per segment stay a small overhead; a multiple of ROWS (minus the 2 lead-in rows)
+        // so the last chunk of a segment wastes < ROWS rows.
+        const int64_t resident = (int64_t)sms * per_sm;
+        int64_t want_segs = (resident * 8 + g.n_tiles - 1) / g.n_tiles;
+        int64_t seg_rows = (H + want_segs - 1) / (want_segs > 0 ? want_segs : 1);
+        if (seg_rows < 32) seg_rows = 32;
+        if (seg_rows > H) seg_rows = H;
+        seg_rows = ((seg_rows + 2 + ROWS - 1) / ROWS) * ROWS - 2;
+        if (seg_rows < 1) seg_rows = 1;
+        g.seg_rows = (int)seg_rows;
+        g.n_segs = (int)((H + seg_rows - 1) / seg_rows);
+        const int64_t n_tasks = (int64_t)g.n_tiles * g.n_segs;
+        int64_t grid = resident < n_tasks ? resident : n_tasks;
         li.used_tma = 1;
         li.grid = (int)grid;
+        li.block = (WARPS + 1) * 32;
         li.smem_bytes = (int)smem;
-        kern<<<(unsigned)grid, kWarpsPerCta * 32, smem, stream>>>(tmap, prm, outs, g);
+        kern<<<(unsigned)grid, (WARPS + 1) * 32, smem, stream>>>(tmap, prm, outs, g);
     } else {
-        // smaller ring than the TMA path's is not needed: same geometry, cp.async fill
-        constexpr size_t smem = (size_t)kWarpsPerCta * STAGES * ROWS * kBoxW * sizeof(T);
-        auto kern = stencil3_cpasync_kernel<Op, ROWS, STAGES>;
+        constexpr int FR = sizeof(T) == 8 ? 2 : kFallbackRows, FS = kFallbackStages;
+        StripGeom g;
+        g.H = H;
+        g.W = W;
+        g.n_strips = (int)((W + kStripW - 1) / kStripW);
+        const int64_t resident_warps = (int64_t)sms * 2 * kWarpsPerCta;
+        int64_t want_segs = (resident_warps * 8 + g.n_strips - 1) / g.n_strips;
+        int64_t seg_rows = (H + want_segs - 1) / (want_segs > 0 ? want_segs : 1);
+        if (seg_rows < 64) seg_rows = 64;
+        if (seg_rows > H) seg_rows = H;
+        seg_rows = ((seg_rows + 2 + FR - 1) / FR) * FR - 2;
+        if (seg_rows < 1) seg_rows = 1;
+        g.seg_rows = (int)seg_rows;
+        g.n_segs = (int)((H + seg_rows - 1) / seg_rows);
+        const int64_t n_tasks = (int64_t)g.n_strips * g.n_segs;
+        const int64_t ctas_needed = (n_tasks + kWarpsPerCta - 1) / kWarpsPerCta;
+        constexpr size_t smem = (size_t)kWarpsPerCta * FS * FR * kBoxW * sizeof(T);
+        auto kern = stencil3_cpasync_kernel<Op, FR, FS>;
         XRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerCta * 32, smem));
@@ -447,6 +511,7 @@ int launch_stencil3(const typename Op::in_t *in, int64_t in_pitch_bytes, const t
         if (grid > ctas_needed) grid = ctas_needed;
         li.used_tma = 0;
         li.grid = (int)grid;
+        li.block = kWarpsPerCta * 32;
         li.smem_bytes = (int)smem;
         kern<<<(unsigned)grid, kWarpsPerCta * 32, smem, stream>>>(in, in_pitch_bytes / (int64_t)sizeof(T), prm, outs, g,
                                                                 out_vec_ok ? 1 : 0);

@@ -1,9 +1,12 @@
 """xrspatial.zonal.stats on the B200 backend (reference: zonal.py:422-667).
 
-One streaming pass of xrs_zonal_partials_ex produces per-zone count / sum / sum-of-squares /
-min / max partials; mean, std (ddof=0) and var are finalised from
-them in float64 on the host.  With `comm` (a torch.distributed process group) the partials of
-row-striped rasters are combined with AllReduce before finalisation.
+One streaming pass (xrs_zonal_hash_accumulate) discovers the zone ids and produces per-zone count /
+sum / sum-of-squares / min / max partials; mean, std (ddof=0) and var are finalised from them in
+float64.  `majority` counts (zone, value) pairs in a second pass (hash table; a device sort when
+the values are too varied for the table).  Custom callables (`stats_funcs` given as a dict, exactly
+like the reference: zonal.py:640-642) run per zone on the zone's valid values, grouped on the device
+by one sort.  With `comm` (a torch.distributed process group) the partials of row-striped rasters
+are combined with AllReduce before finalisation.
 """
 import ctypes
 
@@ -100,7 +103,11 @@ def hash_partials(zones_t, values_t, nodata_values=None, comm=None, cap=1 << 16)
     return ids[order], {n: a[order] for n, a in part.items()}, pivot
 
 
-def pair_counts(zones_t, values_t, nodata_values=None, comm=None, cap=1 << 20):
+class _PairTableOverflow(Exception):
+    """more distinct (zone, value) pairs than the hash table is allowed to grow to"""
+
+
+def pair_counts(zones_t, values_t, nodata_values=None, comm=None, cap=1 << 20, max_cap=1 << 26):
     """(zone ids int64, values float64, counts int64) of every distinct valid (zone, value) pair:
     one pass of xrs_zonal_pair_count over (int32 zone, float32 value) pairs."""
     import torch
@@ -117,7 +124,7 @@ def pair_counts(zones_t, values_t, nodata_values=None, comm=None, cap=1 << 20):
         finite_zone = torch.isfinite(zones_t) if zones_t.dtype.is_floating_point else None
     else:
         zi, finite_zone = zones_t, None
-    vf = values_t.to(torch.float32)
+    vf = values_t.to(torch.float32) + 0.0              # -0.0 and 0.0 are one value (np.unique)
     if values_t.dtype != torch.float32 and not bool(((vf.to(values_t.dtype) == values_t) | ~torch.isfinite(values_t)).all()):
         raise NotImplementedError("'majority' needs values that are exact in float32")
     if finite_zone is not None:
@@ -137,9 +144,9 @@ def pair_counts(zones_t, values_t, nodata_values=None, comm=None, cap=1 << 20):
                       0.0 if nodata_values is None else float(nodata_values), P(keys), P(count), cap, P(ovf), st)
         if int(ovf.item()) == 0:
             break
-        if cap >= (1 << 26):
-            raise NotImplementedError("too many distinct (zone, value) pairs for 'majority'")
-        cap *= 8
+        if cap >= max_cap:
+            raise _PairTableOverflow()
+        cap = min(cap * 16, max_cap)
     used = torch.nonzero(keys != _EMPTY_KEY).reshape(-1)
     k = keys[used].cpu().numpy()
     c = count[used].cpu().numpy()
@@ -156,13 +163,92 @@ def pair_counts(zones_t, values_t, nodata_values=None, comm=None, cap=1 << 20):
     return zone, val, c
 
 
-def majority_by_zone(zones_t, values_t, nodata_values=None, comm=None):
-    """dict zone id -> majority value (most frequent valid value, smallest on ties)."""
-    zone, val, c = pair_counts(zones_t, values_t, nodata_values, comm)
-    order = np.lexsort((val, -c, zone))      # per zone: highest count first, then smallest value
-    zone, val = zone[order], val[order]
-    first = np.r_[True, zone[1:] != zone[:-1]]
-    return dict(zip(zone[first].tolist(), val[first].tolist()))
+def _total_order_bits(v32):
+    """float32 tensor -> int64 keys in [0, 2^32) whose integer order is the float order."""
+    import torch
+    bits = v32.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    return torch.where(bits >= 0x80000000, 0xFFFFFFFF - bits, bits + 0x80000000)
+
+
+def _majority_by_sort(zidx, vals, n_zones):
+    """Majority per zone by one device sort.  zidx: int64 zone index per valid cell (0..n_zones-1),
+    vals: the cells' values (float32: keyed by their order-preserving bit pattern; float64: keyed by
+    their rank among the distinct values).  Returns a float64 numpy array of length n_zones (NaN for
+    zones without cells): the most frequent value, smallest on ties (zonal.py:56-68)."""
+    import torch
+    out = np.full(n_zones, np.nan)
+    if zidx.numel() == 0:
+        return out
+    if vals.dtype == torch.float32:
+        vkey, table = _total_order_bits(vals), None
+        span = 1 << 32
+    else:
+        table, vkey = torch.unique(vals, return_inverse=True)   # sorted distinct values, ranks
+        span = int(table.numel())
+    keys = zidx * span + vkey
+    del vkey
+    keys = torch.sort(keys).values
+    uniq, cnt = torch.unique_consecutive(keys, return_counts=True)
+    del keys
+    zone = torch.div(uniq, span, rounding_mode="floor")
+    zid, zinv = torch.unique_consecutive(zone, return_inverse=True)
+    best = torch.zeros(zid.numel(), dtype=cnt.dtype, device=cnt.device).scatter_reduce_(0, zinv, cnt, "amax")
+    pos = torch.arange(uniq.numel(), device=uniq.device)
+    pos = torch.where(cnt == best[zinv], pos, torch.full_like(pos, uniq.numel()))
+    first = torch.full((zid.numel(),), uniq.numel(), dtype=pos.dtype, device=pos.device).scatter_reduce_(0, zinv, pos, "amin")
+    vk = uniq[first] - zid * span
+    if table is None:
+        b = torch.where(vk >= 0x80000000, vk - 0x80000000, 0xFFFFFFFF - vk)
+        win = b.cpu().numpy().astype(np.uint32).view(np.float32).astype(np.float64)
+    else:
+        win = table[vk].to(torch.float64).cpu().numpy()
+    out[zid.cpu().numpy()] = win
+    return out
+
+
+def majority_by_zone(zones_t, values_t, unique_zones, nodata_values=None, comm=None):
+    """float64 numpy array aligned with `unique_zones` (the sorted distinct finite zone ids): per zone
+    the most frequent valid value, smallest on ties, NaN for zones without valid cells (zonal.py:56-68
+    `_stats_majority` = np.unique + argmax).
+
+    int32 zones with float32-exact values take the (zone, value) pair-count kernel; anything else
+    (non-integer or wide zone ids, float64 values that float32 cannot hold, more distinct pairs than
+    the table may grow to) is grouped by one device sort."""
+    import torch
+    uz = np.asarray(unique_zones)
+    out = np.full(len(uz), np.nan)
+    if len(uz) == 0:
+        return out
+    vf = values_t.to(torch.float32)
+    exact32 = values_t.dtype == torch.float32 or \
+        bool(((vf.to(values_t.dtype) == values_t) | ~torch.isfinite(values_t)).all())
+    if zones_t.dtype == torch.int32 and exact32:
+        try:
+            zone, val, c = pair_counts(zones_t, values_t, nodata_values, comm, max_cap=1 << 24)
+            order = np.lexsort((val, -c, zone))      # per zone: highest count first, then smallest value
+            zone, val = zone[order], val[order]
+            first = np.r_[True, zone[1:] != zone[:-1]]
+            pos = np.searchsorted(uz.astype(np.int64), zone[first])
+            ok = (pos < len(uz)) & (uz.astype(np.int64)[np.minimum(pos, len(uz) - 1)] == zone[first])
+            out[pos[ok]] = val[first][ok]
+            return out
+        except _PairTableOverflow:
+            pass
+    if comm is not None:
+        raise NotImplementedError("'majority' over row stripes needs int32 zones and categorical float32-exact "
+                                  "values (the sort-based path is single-GPU)")
+    z = zones_t.reshape(-1)
+    v = (vf if exact32 else values_t.to(torch.float64)).reshape(-1) + 0.0   # -0.0 and 0.0 are one value
+    ok = torch.isfinite(v)
+    if nodata_values is not None:
+        ok &= v != float(nodata_values)
+    ids_t = torch.as_tensor(uz.astype(np.float64), device=z.device)
+    zf = z.to(torch.float64)
+    if z.dtype.is_floating_point:
+        ok &= torch.isfinite(z)
+    idx = torch.searchsorted(ids_t, zf).clamp_(max=len(uz) - 1)
+    ok &= ids_t[idx] == zf
+    return _majority_by_sort(idx[ok], v[ok], len(uz))
 
 
 def allreduce_tables(ids, part, dev, comm):
@@ -296,9 +382,8 @@ def _stats_device(zones, values, zone_ids, stats_funcs, nodata_values, return_ty
     pivot = np.full(len(sel), pivot0)
     cols = finalize(part, pivot, [s for s in names if s not in ("std", "var", "majority")])
     if "majority" in names:
-        maj = majority_by_zone(zt, vt, nodata_values, comm=comm)
-        cols["majority"] = np.array([maj.get(int(z), np.nan) if float(z).is_integer() else np.nan for z in sel],
-                                    dtype=np.float64)
+        maj = majority_by_zone(zt, vt, unique_zones, nodata_values, comm=comm)
+        cols["majority"] = maj if zone_ids is None else maj[pos]
     sv = [s for s in names if s in ("std", "var")]
     if sv:
         if vt.dtype == torch.float64 and len(sel):
@@ -315,18 +400,78 @@ def _stats_device(zones, values, zone_ids, stats_funcs, nodata_values, return_ty
         for s in names:
             d[s] = cols[s]
         return pd.DataFrame(d)
-    # broadcast every stat back onto the raster (zonal.py:313-331)
-    H, W = vt.shape
-    out = torch.full((len(names), H * W), float("nan"), dtype=torch.float64, device=vt.device)
+    out = _broadcast_back(cols, names, sel, zt, vt.shape, vt.device)
+    return like_container(out, values)
+
+
+def _broadcast_back(cols, names, sel, zt, shape, device):
+    """(len(names), H, W) float64 tensor: every statistic broadcast onto its zone's cells, NaN
+    elsewhere (zonal.py:313-331)."""
+    import torch
+    H, W = shape
+    out = torch.full((len(names), H * W), float("nan"), dtype=torch.float64, device=device)
     if len(sel):
-        ids_t = torch.as_tensor(np.asarray(sel, dtype=np.float64), device=vt.device)
+        ids_t = torch.as_tensor(np.asarray(sel, dtype=np.float64), device=device)
         zf = zt.reshape(-1).to(torch.float64)
         idx = torch.searchsorted(ids_t, zf).clamp_(max=len(sel) - 1)
         hit = ids_t[idx] == zf
         for i, s in enumerate(names):
-            table = torch.as_tensor(cols[s], device=vt.device)
+            table = torch.as_tensor(np.asarray(cols[s], dtype=np.float64), device=device)
             out[i] = torch.where(hit, table[idx], out[i])
-    return like_container(out.reshape(len(names), H, W), values)
+    return out.reshape(len(names), H, W)
+
+
+def _stats_custom(zones, values, zone_ids, stats_funcs, nodata_values, return_type='pandas.DataFrame',
+                  host=False):
+    """`stats_funcs` given as a dict of callables (zonal.py:640-642): the reference groups the cells
+    by zone with an argsort and calls every function on the zone's valid values
+    (`_calc_stats`, zonal.py:144-163).  Same here, with the grouping done by one stable device
+    sort; the callables receive the zone's values in the raster's dtype -- numpy arrays for numpy
+    rasters (`host`), device tensors otherwise -- and must return a scalar."""
+    import torch
+    zt = _prepare(as_device_tensor(zones), (torch.int32, torch.int64, torch.float32, torch.float64))
+    vt = as_device_tensor(values).contiguous()
+    if len(vt.shape) > 2:
+        raise TypeError('3D inputs not supported for the device backend')
+    for name, f in stats_funcs.items():
+        if not callable(f):
+            raise ValueError(name)
+    z = zt.reshape(-1)
+    v = vt.reshape(-1)
+    zfinite = torch.isfinite(z) if z.dtype.is_floating_point else None
+    unique_zones = torch.unique(z[zfinite] if zfinite is not None else z).cpu().numpy()
+    if zone_ids is None:
+        sel = unique_zones
+    else:
+        sel = np.array([zz for zz in np.unique(zone_ids) if zz in unique_zones], dtype=unique_zones.dtype)
+    ok = torch.isfinite(v) if v.dtype.is_floating_point else torch.ones_like(v, dtype=torch.bool)
+    if nodata_values is not None:
+        ok &= v != nodata_values
+    if zfinite is not None:
+        ok &= zfinite
+    zk, vk = z[ok], v[ok]
+    order = torch.argsort(zk, stable=True)
+    zs, vs = zk[order], vk[order]
+    present, counts = torch.unique_consecutive(zs, return_counts=True)
+    present, counts = present.cpu().numpy(), counts.cpu().numpy()
+    starts = np.concatenate([[0], np.cumsum(counts)[:-1]]) if len(counts) else np.zeros(0, np.int64)
+    where = {zz: (int(a), int(a + c)) for zz, a, c in zip(present.tolist(), starts, counts)}
+    groups = vs.cpu().numpy() if host else vs
+    cols = {}
+    for name, func in stats_funcs.items():
+        col = np.full(len(sel), np.nan)
+        for i, zz in enumerate(sel.tolist()):
+            if zz in where:
+                a, b = where[zz]
+                col[i] = float(func(groups[a:b]))
+        cols[name] = col
+    names = list(stats_funcs.keys())
+    if return_type == 'pandas.DataFrame':
+        d = {"zone": sel}
+        d.update({n: cols[n] for n in names})
+        return pd.DataFrame(d)
+    out = _broadcast_back(cols, names, sel, zt, vt.shape, vt.device)
+    return out.cpu().numpy() if host else like_container(out, values)
 
 
 def _stats_host(zones, values, zone_ids, stats_funcs, nodata_values, return_type='pandas.DataFrame'):
@@ -334,23 +479,28 @@ def _stats_host(zones, values, zone_ids, stats_funcs, nodata_values, return_type
     import torch
     zt = torch.from_numpy(np.ascontiguousarray(zones)).cuda()
     vt = torch.from_numpy(np.ascontiguousarray(values)).cuda()
-    res = _stats_device(zt, vt, zone_ids, stats_funcs, nodata_values, return_type)
-    if return_type != 'pandas.DataFrame':
-        res = res.cpu().numpy()
+    if isinstance(stats_funcs, dict):
+        res = _stats_custom(zt, vt, zone_ids, stats_funcs, nodata_values, return_type, host=True)
     else:
+        res = _stats_device(zt, vt, zone_ids, stats_funcs, nodata_values, return_type)
+        if return_type != 'pandas.DataFrame':
+            res = res.cpu().numpy()
+    if return_type == 'pandas.DataFrame':
         res["zone"] = res["zone"].astype(np.asarray(zones).dtype)
     return res
 
 
 def stats(zones, values, zone_ids=None,
-          stats_funcs=["mean", "max", "min", "sum", "std", "var", "count"],
+          stats_funcs=["mean", "max", "min", "sum", "std", "var", "count", "majority"],
           nodata_values=None, return_type='pandas.DataFrame', comm=None):
-    """Per-zone summary statistics (zonal.py:422-667).
+    """Per-zone summary statistics (zonal.py:422-667), same signature and defaults.
 
-    Differences from the reference, all explicit: `stats_funcs` must name built-in statistics
-    (custom callables cannot run on the device); `majority` costs a second pass (a (zone, value)
-    pair histogram) and is therefore not in the default list -- name it to get it.  `comm` (optional torch.distributed group) marks `zones`
-    and `values` as this rank's row stripe of a larger raster.
+    `stats_funcs` as a list names built-in statistics: they come from one streaming pass over the
+    raster (`majority` adds a second pass, so leave it out of the list when it is not needed).
+    `stats_funcs` as a dict maps column names to callables, which are run per zone like the
+    reference does (no built-in is ever substituted for a callable).  `comm` (optional
+    torch.distributed group, not in the reference) marks `zones` and `values` as this rank's row
+    stripe of a larger raster; custom callables are not available over stripes.
     """
     if isinstance(values, Dataset):
         if return_type != 'pandas.DataFrame':
@@ -376,24 +526,29 @@ def stats(zones, values, zone_ids=None,
         if not ok:
             raise ValueError("`%s` must be an array of integers or floats." % nm)
 
-    if isinstance(stats_funcs, dict):
-        bad = [k for k, f in stats_funcs.items() if k not in _DEFAULT_STATS]
-        if bad:
-            raise NotImplementedError("custom statistics %r cannot run on the B200 backend" % (bad,))
-        names = list(stats_funcs.keys())
-    else:
-        names = list(stats_funcs)
-    for s in names:
-        if s not in _DEFAULT_STATS:
-            raise ValueError(f"Invalid stat name. {s} option not supported.")
+    if isinstance(stats_funcs, list):
+        for s in stats_funcs:
+            if s not in _DEFAULT_STATS:
+                raise ValueError(f"Invalid stat name. {s} option not supported.")
+        funcs = list(stats_funcs)
+        names = funcs
+    elif isinstance(stats_funcs, dict):
+        funcs = dict(stats_funcs)
+        names = list(funcs.keys())
+        if comm is not None:
+            raise NotImplementedError("custom statistics cannot be combined across row stripes; "
+                                      "name built-in statistics in a list when `comm` is given")
+    else:  # the reference falls through to an UnboundLocalError here; say what is wrong instead
+        raise TypeError("`stats_funcs` must be a list of statistic names or a dict of callables")
 
     if comm is not None:
-        result = _stats_device(zones.data, values.data, zone_ids, names, nodata_values, return_type, comm)
+        result = _stats_device(zones.data, values.data, zone_ids, funcs, nodata_values, return_type, comm)
     else:
+        device = _stats_custom if isinstance(funcs, dict) else _stats_device
         mapper = ArrayTypeFunctionMapping(
             numpy_func=lambda *a: _stats_host(*a, return_type=return_type),
-            cupy_func=lambda *a: _stats_device(*a, return_type=return_type))
-        result = mapper(values)(zones.data, values.data, zone_ids, names, nodata_values)
+            cupy_func=lambda *a: device(*a, return_type=return_type))
+        result = mapper(values)(zones.data, values.data, zone_ids, funcs, nodata_values)
 
     if return_type == 'xarray.DataArray':
         coords = {'stats': names}
@@ -456,7 +611,10 @@ def crosstab(zones, values, zone_ids=None, cat_ids=None, layer=None, agg="count"
     zt = _prepare(zt, (torch.int32, torch.int64, torch.float32, torch.float64))
     vt_f = vt.contiguous() if vt.dtype in (torch.float32, torch.float64) else vt.to(torch.float64)
     unique_zones, _, _ = hash_partials(zt, vt_f, None, comm=comm)
-    pz, pv, pc = pair_counts(zt, vt_f, nodata_values, comm=comm)
+    try:
+        pz, pv, pc = pair_counts(zt, vt_f, nodata_values, comm=comm)
+    except _PairTableOverflow:
+        raise NotImplementedError("crosstab: more than 64M distinct (zone, category) pairs")
     vdtype = np.dtype(str(vt.dtype).replace("torch.", "")) if not isinstance(values.data, np.ndarray) else values.data.dtype
     unique_cats = np.unique(pv).astype(vdtype)
     if cat_ids is None:
