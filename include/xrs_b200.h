@@ -212,6 +212,18 @@ int xrs_zonal_hash_accumulate(const void *values, int values_dtype, const void *
                               double *s2, double *vmin, double *vmax, int cap, int *overflow,
                               xrs_stream_t s);
 
+/* The whole single-pass group-by behind one call, with no host round trip in the middle: samples the
+ * pivot on the device (unless use_pivot_hint: row stripes must share one pivot), initialises the table,
+ * accumulates, then compacts the used slots into `packed` (device, 3 + 6 * max_out doubles):
+ *   packed[0] = used slots, packed[1] = table overflowed (grow `cap` and retry), packed[2] = pivot,
+ *   then 6 rows of max_out: key bit patterns, count (int64 bit patterns), s1, s2, min, max, in any
+ *   order.  Slots beyond max_out are dropped (packed[0] > max_out tells; read the table instead).
+ * flags: 2 device ints of scratch.  Replaces the sort + per-zone reductions of zonal.py:280-332. */
+int xrs_zonal_hash_run(const void *values, int values_dtype, const void *zones, int zones_dtype, int64_t n,
+                       int64_t row_len, int has_nodata, double nodata, int use_pivot_hint, double pivot_hint,
+                       int64_t *keys, int64_t *count, double *s1, double *s2, double *vmin, double *vmax, int cap,
+                       double *packed, int max_out, int *flags, xrs_stream_t s);
+
 /* `majority` (zonal.py:56-68): counts (zone, value) pairs of float32 values / int32 zones into
  * a hash table (keys/count of `cap` entries, initialised with xrs_zonal_hash_init; key =
  * (zone << 32) | float32 bits of the value, -0.0 folded into +0.0).  The caller picks the most
@@ -241,6 +253,15 @@ int xrs_host_stencil(int op, const void *in, void *out, int64_t H, int64_t W, co
  * (xrs_surface_typed behind the same pipeline; needs W % 4 == 0): the raw cells cross PCIe. */
 int xrs_host_surface_typed(int op, const void *in, int in_dtype, float *out, int64_t H, int64_t W,
                            const double *p, int device);
+/* The same two entry points over SEVERAL devices: output rows are cut into one stripe per listed
+ * device, each stripe runs the chunk pipeline on its own host thread and PCIe link; the halo rows
+ * of a stripe come from the host raster, so there is no device-to-device traffic.  This is the
+ * reference's dask.map_overlap(depth=r, boundary=nan) over row blocks (slope.py:94-97,
+ * focal.py:72-75) for host rasters.  devices: CUDA ordinals, each at most once. */
+int xrs_host_stencil_multi(int op, const void *in, void *out, int64_t H, int64_t W, const double *p,
+                           const double *aux, int naux, const int *devices, int n_devices);
+int xrs_host_surface_typed_multi(int op, const void *in, int in_dtype, float *out, int64_t H, int64_t W,
+                                 const double *p, const int *devices, int n_devices);
 /* frees the per-device staging buffers the host path keeps between calls */
 int xrs_host_release(int device);
 /* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers that want

@@ -12,7 +12,7 @@ t = torch.empty((side, side), dtype=torch.float32, device="cuda")
 _lib.call("xrs_synth_terrain_f32", ctypes.c_void_p(t.data_ptr()), side * 4, side, side, 0, 0, 1235, 0.0, 4000.0,
           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
 agg = xb.DataArray(t, dims=("y", "x"), attrs={"res": (30.0, 30.0)})
-fns = {"slope": xb.slope, "hillshade": xb.hillshade, "mean": xb.mean, "aspect": xb.aspect, "curvature": xb.curvature}
+fns = {"slope": xb.slope, "hillshade": xb.hillshade, "mean": xb.mean, "aspect": xb.aspect, "curvature": xb.curvature, "suite": xb.surface_suite}
 for _ in range(reps):
     for o in ops:
         fns[o](agg)

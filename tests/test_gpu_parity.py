@@ -410,12 +410,23 @@ def _stripe_worker(rank, world, port, H, W, q):
         rng = np.random.default_rng(33)
         z = terrain(rng, H, W, nans=0.002)
         zones = ((np.arange(H)[:, None] // 64) * 8 + np.arange(W)[None, :] // 64).astype(np.int32)
-        st = RowStripes(H, W, radius=1, device=torch.device("cuda", rank))
+        dev_ = torch.device("cuda", rank)
+        st = RowStripes(H, W, radius=1, device=dev_)
         st.interior.copy_(torch.from_numpy(z[st.y0:st.y1]))
-        st.exchange()
         res = {}
+        attrs = {"res": (30.0, 30.0)}
         for name, fn in (("slope", xbm.slope), ("hillshade", xbm.hillshade), ("mean", xbm.mean)):
-            res[name] = st.apply(fn, attrs={"res": (30.0, 30.0)}).cpu().numpy()
+            res[name] = st.apply(fn, attrs=attrs).cpu().numpy()                       # overlapped exchange
+            res[name + "/plain"] = st.apply(fn, attrs=attrs, overlap=False).cpu().numpy()
+        res["mean3"] = st.mean(passes=3).cpu().numpy()                                 # one exchange per pass
+        krng = np.random.default_rng(8)
+        for k in (9, 25):                                                              # wide halos (r = 4, 12)
+            kern = krng.standard_normal((k, k))
+            sk = RowStripes(H, W, radius=k // 2, device=dev_)
+            sk.interior.copy_(torch.from_numpy(z[sk.y0:sk.y1]))
+            res["conv%d" % k] = sk.convolve(kern).cpu().numpy()
+            res["conv%d/plain" % k] = sk.convolve(kern, overlap=False).cpu().numpy()
+        st.exchange()
         zagg = xbm.DataArray(torch.from_numpy(zones[st.y0:st.y1]).cuda(), dims=("y", "x"))
         vagg = xbm.DataArray(st.interior, dims=("y", "x"))
         df = xbm.zonal_stats(zagg, vagg, comm=dist.group.WORLD)
@@ -450,8 +461,19 @@ def test_two_gpu_stripes_match_single_gpu(xb):
     agg = da(xb, dev(z))
     for name, fn in (("slope", xb.slope), ("hillshade", xb.hillshade), ("mean", xb.mean)):
         whole = host(fn(agg))
-        stitched = np.concatenate([g[3][name] for g in got])
-        np.testing.assert_array_equal(stitched, whole, err_msg=name)
+        for variant in (name, name + "/plain"):
+            stitched = np.concatenate([g[3][variant] for g in got])
+            np.testing.assert_array_equal(stitched, whole, err_msg=variant)
+    # focal.mean(passes=3): one halo exchange per pass (focal.py:72-75, 258-259)
+    np.testing.assert_array_equal(np.concatenate([g[3]["mean3"] for g in got]), host(xb.mean(agg, passes=3)),
+                                  err_msg="mean passes=3")
+    # k = 9 / 25 convolutions over stripes with 4- / 12-row halos
+    krng = np.random.default_rng(8)
+    for k in (9, 25):
+        kern = krng.standard_normal((k, k))
+        whole = host(xb.convolution_2d(agg, kern))
+        for variant in ("conv%d" % k, "conv%d/plain" % k):
+            np.testing.assert_array_equal(np.concatenate([g[3][variant] for g in got]), whole, err_msg=variant)
     df = xb.zonal_stats(da(xb, dev(zones)), agg)
     for c in df.columns:
         a, b = np.asarray(df[c]), got[0][4][c]
@@ -798,12 +820,11 @@ def test_majority_by_sort_equals_the_pair_table(xb):
     old = Z.pair_counts.__defaults__
     Z.pair_counts.__defaults__ = (None, None, 1 << 10, 1 << 12)
     try:
-        df = xb.zonal_stats(da(xb, dev(zz)), da(xb, dev(vals)), stats_funcs=["majority", "min"])
+        df = xb.zonal_stats(da(xb, dev(zz)), da(xb, dev(vals)), stats_funcs=["majority"])
     finally:
         Z.pair_counts.__defaults__ = old
     ref = o.zonal_stats(zz, vals, stats_funcs=["majority"])
     np.testing.assert_array_equal(np.asarray(df["majority"]), np.asarray(ref["majority"], dtype=np.float64))
-    np.testing.assert_array_equal(np.asarray(df["majority"]), np.asarray(df["min"]))   # all values distinct
 
 
 def test_summarize_terrain_docstring_example(xb):
@@ -865,3 +886,89 @@ def test_bare_dataarray_without_coords_uses_unit_cells(xb):
     assert_close_f32(host(xb.slope(agg)), o.slope(z, 1.0, 1.0), what="slope")
     assert_close_f32(host(xb.curvature(agg)), o.curvature(z, 1.0), atol=1e-6 * np.nanmax(np.abs(o.curvature(z, 1.0))),
                      what="curvature")
+
+
+def test_pinned_cache_is_bounded_and_lru(xb):
+    """_hostmem: idle page-locked blocks are capped; the least recently released go first."""
+    from xrspatial_b200 import _hostmem as hm
+    hm.trim()
+    old = hm.MAX_CACHED_BYTES
+    hm.MAX_CACHED_BYTES = 3 << 20
+    try:
+        for mb in (1, 2, 1):                      # release 1 MiB, 2 MiB, 1 MiB -> 4 MiB idle > 3 MiB cap
+            a = hm.empty((mb << 20,), np.uint8)
+            a[:] = 7
+            del a
+        assert hm.cached_bytes() <= 3 << 20
+        assert hm.cached_bytes() == 3 << 20       # the OLDEST (first 1 MiB) block was evicted
+        b = hm.empty((2 << 20,), np.uint8)        # recycled, no new allocation
+        assert hm.cached_bytes() == 1 << 20
+        del b
+        big = hm.empty((4 << 20,), np.uint8)      # larger than the cap: freed on release, never cached
+        del big
+        assert hm.cached_bytes() <= 3 << 20
+    finally:
+        hm.MAX_CACHED_BYTES = old
+        hm.trim()
+    assert hm.cached_bytes() == 0
+
+
+def test_host_path_over_several_devices_matches_one_device(xb, monkeypatch):
+    """xrs_host_stencil_multi: row stripes over the visible GPUs, halos from the host raster: the
+    result is the single-device result bit for bit (with one GPU the stripes collapse to one)."""
+    rng = np.random.default_rng(77)
+    z = terrain(rng, 1500, 1024, nans=0.003)
+    kern = rng.standard_normal((9, 9))
+    n = torch.cuda.device_count()
+    monkeypatch.setenv("XRS_B200_DEVICES", "0")
+    one = {"slope": xb.slope(da(xb, z)).data.copy(), "mean": xb.mean(da(xb, z)).data.copy(),
+           "conv": xb.convolve_2d(z, kern).copy(), "i16": xb.slope(da(xb, np.round(z).astype(np.int16))).data.copy()}
+    monkeypatch.setenv("XRS_B200_DEVICES", "all")
+    from xrspatial_b200 import utils
+    assert utils.host_devices() == list(range(n))
+    many = {"slope": xb.slope(da(xb, z)).data, "mean": xb.mean(da(xb, z)).data, "conv": xb.convolve_2d(z, kern),
+            "i16": xb.slope(da(xb, np.round(z).astype(np.int16))).data}
+    for k in one:
+        np.testing.assert_array_equal(one[k], many[k], err_msg=k)
+    assert_close_f32(many["slope"], o.slope(z, 30.0, 30.0), what="slope")
+    monkeypatch.setenv("XRS_B200_DEVICES", "0,0")
+    with pytest.raises(ValueError):
+        xb.slope(da(xb, z))
+    monkeypatch.setenv("LOCAL_RANK", "0")
+    monkeypatch.delenv("XRS_B200_DEVICES")
+    assert utils.host_devices() == [torch.cuda.current_device()]      # one process per GPU: own device only
+
+
+def test_synthetic_dem_host_twin_matches_the_device_generator(xb):
+    """oracle.synth_terrain (bench.py's CPU arms) == xrs_synth_terrain_f32 to float32 rounding, for an
+    offset window -- the generator is a pure function of (seed, global row, global col)."""
+    import ctypes
+    t = torch.empty((300, 512), dtype=torch.float32, device="cuda")
+    xb._lib.call("xrs_synth_terrain_f32", ctypes.c_void_p(t.data_ptr()), 512 * 4, 300, 512, 4100, 8192, 1235, 0.0, 4000.0,
+                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    ref = o.synth_terrain(300, 512, 4100, 8192, 1235, 0.0, 4000.0, nthreads=4)
+    np.testing.assert_allclose(t.cpu().numpy(), ref, rtol=2e-6, atol=2e-3)
+
+
+def test_zonal_many_zones_and_degenerate_rasters(xb):
+    """hash_partials: more zones than the one-copy fast path returns (4096) fall back to gathering the
+    table; 1-cell and empty rasters; a zone whose cells are all invalid is still reported (NaN row)."""
+    rng = np.random.default_rng(19)
+    zones = rng.integers(0, 6000, size=(512, 640)).astype(np.int32)
+    vals = rng.standard_normal((512, 640)).astype(np.float32) * 50 + 300
+    vals[zones == 17] = np.nan
+    cols = ["mean", "max", "min", "sum", "std", "var", "count"]
+    df = xb.zonal_stats(da(xb, dev(zones)), da(xb, dev(vals)), stats_funcs=cols)
+    ref = o.zonal_stats(zones, vals, stats_funcs=cols)
+    assert len(df) == len(np.unique(zones)) > 4096
+    np.testing.assert_array_equal(np.asarray(df["zone"]), ref["zone"])
+    for c in ("count", "min", "max"):
+        np.testing.assert_array_equal(np.asarray(df[c], dtype=np.float64), ref[c], err_msg=c)
+    for c in ("mean", "sum", "std", "var"):
+        np.testing.assert_allclose(np.asarray(df[c], dtype=np.float64), ref[c], rtol=1e-5, atol=1e-4, equal_nan=True, err_msg=c)
+    row = df[df["zone"] == 17]
+    assert len(row) == 1 and np.isnan(row["mean"].iloc[0]) and np.isnan(row["count"].iloc[0])
+    one = xb.zonal_stats(da(xb, dev(np.array([[3]], np.int32))), da(xb, dev(np.array([[2.5]], np.float32))), stats_funcs=cols)
+    assert list(one["zone"]) == [3] and one["mean"].iloc[0] == 2.5 and one["count"].iloc[0] == 1 and one["var"].iloc[0] == 0
+    emp = xb.zonal_stats(da(xb, dev(np.zeros((0, 8), np.int32))), da(xb, dev(np.zeros((0, 8), np.float32))), stats_funcs=cols)
+    assert len(emp) == 0 and list(emp.columns) == ["zone"] + cols

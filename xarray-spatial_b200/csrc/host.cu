@@ -8,7 +8,16 @@
 // treats the chunk view as a raster of its own, so its first/last r output rows are only
 // correct when they coincide with the real raster edge -- interior halo rows are simply
 // not copied back.  Host buffers may be pageable (works, slower) or pinned (xrs_host_alloc).
+//
+// Several GPUs (xrs_host_stencil_multi): the output rows are cut into one stripe per device and
+// every device runs the pipeline above on its stripe from its own host thread -- one PCIe link
+// each, no device-to-device traffic at all, because a stripe's halo rows come straight from the
+// host raster like any chunk's.  This is the reference's `dask.map_overlap(depth=r)` over row
+// blocks (slope.py:94-97) with the blocks being PCIe-sized.
 #include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "common.cuh"
 
@@ -78,9 +87,11 @@ static int run_op(int op, int in_dtype, const void *din, void *dout, int64_t pit
 
 using namespace xrs;
 
+// Output rows [y_begin, y_end) of the H x W raster on `device`.
 static int host_pipeline(int op, int in_dtype, const void *in, void *out, int64_t H, int64_t W, const double *p,
-                         const double *aux, int naux, int device) {
-    if (H <= 0 || W <= 0) return XRS_OK;
+                         const double *aux, int naux, int device, int64_t y_begin = 0, int64_t y_end = -1) {
+    if (y_end < 0) y_end = H;
+    if (H <= 0 || W <= 0 || y_end <= y_begin) return XRS_OK;
     XRS_REQUIRE(in && out, "NULL host pointer");
     XRS_REQUIRE(device >= 0 && device < 16, "device index out of range");
     XRS_REQUIRE(op >= XRS_OP_SLOPE && op <= XRS_OP_FOCAL_MEAN_F32_F64, "unknown op");
@@ -111,15 +122,16 @@ static int host_pipeline(int op, int in_dtype, const void *in, void *out, int64_
     // device row pitch: multiple of 16 bytes so the TMA kernels apply whenever W % 4 == 0
     const int64_t row_bytes = W * esz, orow_bytes = W * osz;
     const int64_t pitch = (row_bytes + 15) / 16 * 16, opitch = (orow_bytes + 15) / 16 * 16;
+    const int64_t span = y_end - y_begin;
     int64_t rows = (32LL << 20) / pitch;
     if (rows < 8 * radius + 8) rows = 8 * radius + 8;
-    if (rows > H) rows = H;
-    const int64_t n_chunks = (H + rows - 1) / rows;
+    if (rows > span) rows = span;
+    const int64_t n_chunks = (span + rows - 1) / rows;
     const size_t cap = (size_t)(rows + 2 * radius) * pitch, ocap = (size_t)(rows + 2 * radius) * opitch;
 
     for (int64_t ci = 0; ci < n_chunks && rc == XRS_OK; ++ci) {
         Slot &s = c.slot[ci % 3];
-        const int64_t r0 = ci * rows, r1 = (r0 + rows < H) ? r0 + rows : H;
+        const int64_t r0 = y_begin + ci * rows, r1 = (r0 + rows < y_end) ? r0 + rows : y_end;
         const int64_t a0 = (r0 - radius > 0) ? r0 - radius : 0, a1 = (r1 + radius < H) ? r1 + radius : H;
         const int64_t h = a1 - a0;
         // the slot is free once its previous D2H has finished
@@ -157,6 +169,59 @@ static int host_pipeline(int op, int in_dtype, const void *in, void *out, int64_
 extern "C" int xrs_host_stencil(int op, const void *in, void *out, int64_t H, int64_t W, const double *p,
                                 const double *aux, int naux, int device) {
     return host_pipeline(op, XRS_F32, in, out, H, W, p, aux, naux, device);
+}
+
+// Row stripes over several devices, one host thread and one PCIe link per device.  Errors: the
+// first failing stripe's status and message are returned (the message is copied out of the worker
+// thread, whose thread-local error string the caller cannot see).
+static int host_multi(int op, int in_dtype, const void *in, void *out, int64_t H, int64_t W, const double *p,
+                      const double *aux, int naux, const int *devices, int n_devices) {
+    XRS_REQUIRE(devices != nullptr && n_devices >= 1 && n_devices <= 16, "1 .. 16 devices expected");
+    if (H <= 0 || W <= 0) return XRS_OK;
+    int radius = 1;
+    if (op == XRS_OP_CONVOLVE || op == XRS_OP_FOCAL_STAT) {
+        XRS_REQUIRE(p != nullptr, "kernel parameters missing");
+        radius = (int)p[0] / 2;
+    }
+    // stripes shorter than a few halos are not worth a device
+    int n = n_devices;
+    while (n > 1 && H / n < 8 * radius + 8) --n;
+    if (n == 1) return host_pipeline(op, in_dtype, in, out, H, W, p, aux, naux, devices[0]);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i; ++j) XRS_REQUIRE(devices[i] != devices[j], "device listed twice");
+    std::vector<int> rc(n, XRS_OK);
+    std::vector<std::string> msg(n);
+    std::vector<std::thread> th;
+    const int64_t base = H / n, rem = H % n;
+    int64_t y = 0;
+    for (int i = 0; i < n; ++i) {
+        const int64_t h = base + (i < rem ? 1 : 0);
+        const int64_t y0 = y, y1 = y + h;
+        y = y1;
+        th.emplace_back([&, i, y0, y1] {
+            rc[i] = host_pipeline(op, in_dtype, in, out, H, W, p, aux, naux, devices[i], y0, y1);
+            if (rc[i] != XRS_OK) msg[i] = xrs_last_error_string();
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int i = 0; i < n; ++i)
+        if (rc[i] != XRS_OK) {
+            set_error("device %d: %s", devices[i], msg[i].c_str());
+            return rc[i];
+        }
+    return XRS_OK;
+}
+
+extern "C" int xrs_host_stencil_multi(int op, const void *in, void *out, int64_t H, int64_t W, const double *p,
+                                      const double *aux, int naux, const int *devices, int n_devices) {
+    return host_multi(op, XRS_F32, in, out, H, W, p, aux, naux, devices, n_devices);
+}
+
+extern "C" int xrs_host_surface_typed_multi(int op, const void *in, int in_dtype, float *out, int64_t H, int64_t W,
+                                            const double *p, const int *devices, int n_devices) {
+    XRS_REQUIRE(in_dtype == XRS_F64 || in_dtype == XRS_I32 || in_dtype == XRS_I16 || in_dtype == XRS_U16,
+                "in_dtype must be int16, uint16, int32 or float64");
+    return host_multi(op, in_dtype, in, out, H, W, p, nullptr, 0, devices, n_devices);
 }
 
 // slope / aspect / curvature / hillshade on a HOST raster of int16 / uint16 / int32 / float64 cells:

@@ -29,6 +29,7 @@ struct ZhArgs {
     int64_t n;
     int64_t W;      // row length of the raster (n = H * W); walking DOWN columns keeps runs long
     double pivot;
+    const double *pivot_ptr;   // when not NULL the pivot is read from device memory (xrs_zonal_hash_run)
     int has_nodata;
     double nodata;
     long long *keys;
@@ -207,7 +208,9 @@ template <typename T> __device__ __forceinline__ ZhQuad<T> zh_load(const T *p, i
 }
 
 template <typename VT, typename ZT>
-__global__ void __launch_bounds__(kZhThreads, 3) zonal_hash_kernel(const __grid_constant__ ZhArgs a) {
+__global__ void __launch_bounds__(kZhThreads, 3) zonal_hash_kernel(const __grid_constant__ ZhArgs a_in) {
+    ZhArgs a = a_in;
+    if (a.pivot_ptr != nullptr) a.pivot = *a.pivot_ptr;
     using MM = typename ZhMinMax<VT>::type;
     constexpr int kCap = ZhTable<VT>::kCap;
     extern __shared__ __align__(16) unsigned char zh_smem[];
@@ -482,6 +485,61 @@ __global__ void zonal_hash_init_kernel(long long *keys, unsigned long long *coun
     if (i == 0) *overflow = 0;
 }
 
+// ---- one-call front end: pivot sampling, table compaction and header, all on the device ----------
+// mean of up to 4096 finite samples taken at a regular stride: a shift that keeps sum((v - p)^2)
+// well conditioned (any value works; it only has to be the same for every cell)
+template <typename VT>
+__global__ void __launch_bounds__(256) zonal_pivot_kernel(const VT *__restrict__ v, int64_t n, double *out) {
+    __shared__ double s_sum[256];
+    __shared__ unsigned s_cnt[256];
+    const int64_t samples = n < 4096 ? n : 4096;
+    const int64_t step = n / samples;
+    double acc = 0.0;
+    unsigned cnt = 0u;
+    for (int64_t i = threadIdx.x; i < samples; i += 256) {
+        const double x = (double)v[i * step];
+        if (fabs(x) <= 1.7976931348623157e308) { acc += x; cnt += 1u; }
+    }
+    s_sum[threadIdx.x] = acc;
+    s_cnt[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { s_sum[threadIdx.x] += s_sum[threadIdx.x + o]; s_cnt[threadIdx.x] += s_cnt[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = s_cnt[0] ? s_sum[0] / (double)s_cnt[0] : 0.0;
+}
+
+// used slots -> dense rows of `packed` (6 rows of max_out doubles after a 3-double header), any order
+__global__ void __launch_bounds__(256) zonal_compact_kernel(const long long *keys, const unsigned long long *count,
+                                                            const double *s1, const double *s2, const double *vmin,
+                                                            const double *vmax, int cap, double *packed, int max_out,
+                                                            int *flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap) return;
+    const long long k = keys[i];
+    if (k == kZhEmpty) return;
+    const int pos = atomicAdd(&flags[1], 1);
+    if (pos >= max_out) return;
+    double *row = packed + 3;
+    row[pos] = __longlong_as_double(k);
+    row[max_out + pos] = __longlong_as_double((long long)count[i]);
+    row[2 * max_out + pos] = s1[i];
+    row[3 * max_out + pos] = s2[i];
+    row[4 * max_out + pos] = vmin[i];
+    row[5 * max_out + pos] = vmax[i];
+}
+__global__ void zonal_header_kernel(double *packed, const int *flags, const double *pivot) {
+    packed[0] = (double)flags[1];   // used slots
+    packed[1] = (double)flags[0];   // table overflow
+    packed[2] = *pivot;
+}
+__global__ void zonal_flags_kernel(int *flags, double *pivot_dev, double pivot_hint) {
+    flags[0] = 0;
+    flags[1] = 0;
+    if (pivot_dev) *pivot_dev = pivot_hint;
+}
+
 template <typename VT, typename ZT> static int launch_zh(const ZhArgs &a, cudaStream_t s) {
     const int64_t H = a.n / a.W;
     const int64_t n_tasks = ((a.W + 127) / 128) * ((H + kZhSegRows - 1) / kZhSegRows);
@@ -526,7 +584,8 @@ int xrs_zonal_hash_accumulate(const void *values, int values_dtype, const void *
     XRS_REQUIRE(cap >= 1024 && (cap & (cap - 1)) == 0, "cap must be a power of two >= 1024");
     XRS_REQUIRE(row_len >= 1 && n % row_len == 0, "n must be a multiple of row_len");
     ZhArgs a;
-    a.values = values; a.zones = zones; a.n = n; a.W = row_len; a.pivot = pivot; a.has_nodata = has_nodata; a.nodata = nodata;
+    a.values = values; a.zones = zones; a.n = n; a.W = row_len; a.pivot = pivot; a.pivot_ptr = nullptr;
+    a.has_nodata = has_nodata; a.nodata = nodata;
     a.keys = (long long *)keys; a.count = (unsigned long long *)count; a.s1 = s1; a.s2 = s2; a.vmin = vmin;
     a.vmax = vmax; a.cap = cap; a.overflow = overflow;
     cudaStream_t st = (cudaStream_t)s;
@@ -541,6 +600,49 @@ int xrs_zonal_hash_accumulate(const void *values, int values_dtype, const void *
     if (values_dtype == XRS_F32) { XRS_ZH(float) } else { XRS_ZH(double) }
 #undef XRS_ZH
     return rc;
+}
+
+int xrs_zonal_hash_run(const void *values, int values_dtype, const void *zones, int zones_dtype, int64_t n,
+                       int64_t row_len, int has_nodata, double nodata, int use_pivot_hint, double pivot_hint,
+                       int64_t *keys, int64_t *count, double *s1, double *s2, double *vmin, double *vmax, int cap,
+                       double *packed, int max_out, int *flags, xrs_stream_t s) {
+    XRS_REQUIRE(values && zones && keys && count && s1 && s2 && vmin && vmax && packed && flags, "NULL pointer");
+    XRS_REQUIRE(values_dtype == XRS_F32 || values_dtype == XRS_F64, "values must be float32 or float64");
+    XRS_REQUIRE(zones_dtype >= XRS_F32 && zones_dtype <= XRS_I64, "unknown zones dtype");
+    XRS_REQUIRE(cap >= 1024 && (cap & (cap - 1)) == 0, "cap must be a power of two >= 1024");
+    XRS_REQUIRE(max_out >= 1, "max_out must be positive");
+    XRS_REQUIRE(n >= 1 && row_len >= 1 && n % row_len == 0, "n must be a positive multiple of row_len");
+    cudaStream_t st = (cudaStream_t)s;
+    double *pivot_dev = packed + 2;   // the header's pivot cell doubles as the device-side pivot
+    zonal_flags_kernel<<<1, 1, 0, st>>>(flags, pivot_dev, pivot_hint);
+    if (!use_pivot_hint) {
+        if (values_dtype == XRS_F32) zonal_pivot_kernel<float><<<1, 256, 0, st>>>((const float *)values, n, pivot_dev);
+        else zonal_pivot_kernel<double><<<1, 256, 0, st>>>((const double *)values, n, pivot_dev);
+    }
+    zonal_hash_init_kernel<<<(cap + 255) / 256, 256, 0, st>>>((long long *)keys, (unsigned long long *)count, s1, s2,
+                                                             vmin, vmax, cap, flags);
+    XRS_CUDA(cudaGetLastError());
+    ZhArgs a;
+    a.values = values; a.zones = zones; a.n = n; a.W = row_len; a.pivot = 0.0; a.pivot_ptr = pivot_dev;
+    a.has_nodata = has_nodata; a.nodata = nodata;
+    a.keys = (long long *)keys; a.count = (unsigned long long *)count; a.s1 = s1; a.s2 = s2; a.vmin = vmin;
+    a.vmax = vmax; a.cap = cap; a.overflow = flags;
+    int rc;
+#define XRS_ZH(VT)                                                               \
+    switch (zones_dtype) {                                                       \
+        case XRS_I32: rc = launch_zh<VT, int>(a, st); break;                     \
+        case XRS_I64: rc = launch_zh<VT, long long>(a, st); break;               \
+        case XRS_F32: rc = launch_zh<VT, float>(a, st); break;                   \
+        default: rc = launch_zh<VT, double>(a, st); break;                       \
+    }
+    if (values_dtype == XRS_F32) { XRS_ZH(float) } else { XRS_ZH(double) }
+#undef XRS_ZH
+    if (rc != XRS_OK) return rc;
+    zonal_compact_kernel<<<(cap + 255) / 256, 256, 0, st>>>((const long long *)keys, (const unsigned long long *)count,
+                                                           s1, s2, vmin, vmax, cap, packed, max_out, flags);
+    zonal_header_kernel<<<1, 1, 0, st>>>(packed, flags, pivot_dev);
+    XRS_CUDA(cudaGetLastError());
+    return XRS_OK;
 }
 
 int xrs_zonal_pair_count(const float *values, const int32_t *zones, int64_t n, int64_t row_len, int has_nodata,

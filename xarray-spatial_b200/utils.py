@@ -65,6 +65,34 @@ def host_device_index():
     return int(os.environ.get("XRS_B200_DEVICE", "0"))
 
 
+def host_devices():
+    """CUDA ordinals the host-buffer (numpy) path stripes a raster over.
+
+    XRS_B200_DEVICES = "all" | comma-separated ordinals.  Default: every visible GPU -- one PCIe link
+    per stripe -- unless this process is one rank of a one-process-per-GPU job (LOCAL_RANK set, e.g.
+    under torchrun) or XRS_B200_DEVICE pins a device, in which case only that GPU is used."""
+    spec = os.environ.get("XRS_B200_DEVICES")
+    if spec is None:
+        if "XRS_B200_DEVICE" in os.environ:
+            return [host_device_index()]
+        if "LOCAL_RANK" in os.environ:
+            return [torch.cuda.current_device() if torch is not None and torch.cuda.is_available()
+                    else int(os.environ["LOCAL_RANK"])]
+        spec = "all"
+    if spec.strip().lower() == "all":
+        n = ctypes.c_int(0)
+        _lib.call("xrs_device_count", ctypes.byref(n))
+        return list(range(max(1, n.value)))
+    devs = [int(x) for x in spec.split(",") if x.strip() != ""]
+    if not devs or len(set(devs)) != len(devs):
+        raise ValueError("XRS_B200_DEVICES must list distinct CUDA ordinals, got %r" % spec)
+    return devs
+
+
+def _dev_array(devs):
+    return (ctypes.c_int * len(devs))(*devs), len(devs)
+
+
 def not_implemented_func(agg, *args, messages='Not yet implemented.'):
     raise NotImplementedError(messages)
 
@@ -225,8 +253,9 @@ def run_surface_host(op, data, p=()):
         H, W = d.shape
         out = _hostmem.empty((H, W), np.float32)
         try:
-            _lib.call("xrs_host_surface_typed", _lib.OPS[op], ctypes.c_void_p(d.ctypes.data), code,
-                      ctypes.c_void_p(out.ctypes.data), H, W, _dbl_array(p), host_device_index())
+            devs, nd = _dev_array(host_devices())
+            _lib.call("xrs_host_surface_typed_multi", _lib.OPS[op], ctypes.c_void_p(d.ctypes.data), code,
+                      ctypes.c_void_p(out.ctypes.data), H, W, _dbl_array(p), devs, nd)
             return out
         except NotImplementedError:
             pass
@@ -243,9 +272,9 @@ def run_stencil_host(op, data, p=(), aux=(), out_dtype=np.float32, in_dtype=np.f
     if H == 0 or W == 0:
         return np.empty((H, W), out_dtype)
     out = _hostmem.empty((H, W), out_dtype)
-    _lib.call("xrs_host_stencil", _lib.OPS[op], ctypes.c_void_p(d.ctypes.data),
-              ctypes.c_void_p(out.ctypes.data), H, W, _dbl_array(p), _dbl_array(aux), len(aux),
-              host_device_index())
+    devs, nd = _dev_array(host_devices())
+    _lib.call("xrs_host_stencil_multi", _lib.OPS[op], ctypes.c_void_p(d.ctypes.data),
+              ctypes.c_void_p(out.ctypes.data), H, W, _dbl_array(p), _dbl_array(aux), len(aux), devs, nd)
     return out
 
 

@@ -59,40 +59,54 @@ def _sample_pivot(values_t, comm=None):
     return p0
 
 
+_MAX_OUT = 4096     # zones returned by the one-copy fast path of hash_partials
+
+
 def hash_partials(zones_t, values_t, nodata_values=None, comm=None, cap=1 << 16):
     """One streaming pass that discovers the zone ids and accumulates their partials
-    (xrs_zonal_hash_accumulate).  Returns (ids, part, pivot): ids = sorted unique finite zone
-    values present in the raster (numpy, in the zones dtype), part = dict of numpy arrays aligned
-    with ids (count int64; s1, s2, min, max float64), pivot = the scalar shift of s1/s2.
-    With `comm`, the tables of all ranks are merged by id."""
+    (xrs_zonal_hash_run: pivot sampling, table init, accumulation and compaction are enqueued
+    back to back; ONE device-to-host copy -- a 3-double header + 6 x 4096 doubles -- is the only
+    synchronisation).  Returns (ids, part, pivot): ids = sorted unique finite zone values present
+    in the raster (numpy, in the zones dtype), part = dict of numpy arrays aligned with ids
+    (count int64; s1, s2, min, max float64), pivot = the scalar shift of s1/s2.
+    With `comm`, the tables of all ranks are merged by id (and share one pivot)."""
     import torch
     dev = values_t.device
-    pivot = _sample_pivot(values_t, comm)
+    hint = _sample_pivot(values_t, comm) if comm is not None else None
     P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    if values_t.numel() == 0:
+        zdt = np.float32 if zones_t.dtype == torch.float32 else np.float64 if zones_t.dtype == torch.float64 else \
+            np.int32 if zones_t.dtype == torch.int32 else np.int64
+        e = np.zeros(0)
+        return np.zeros(0, zdt), dict(count=np.zeros(0, np.int64), s1=e, s2=e.copy(), min=e.copy(), max=e.copy()), 0.0
     while True:
-        # one blob: rows = keys, count (int64 bit patterns), s1, s2, min, max; + the overflow flag
+        # one blob: rows = keys, count (int64 bit patterns), s1, s2, min, max
         blob = torch.empty((6, cap), dtype=torch.float64, device=dev)
-        ovf = torch.empty(1, dtype=torch.int32, device=dev)
+        packed = torch.empty(3 + 6 * _MAX_OUT, dtype=torch.float64, device=dev)
+        flags = torch.empty(2, dtype=torch.int32, device=dev)
         keys, count = blob[0].view(torch.int64), blob[1].view(torch.int64)
         with torch.cuda.device(dev):
-            st = stream_ptr(values_t)
-            _lib.call("xrs_zonal_hash_init", P(keys), P(count), P(blob[2]), P(blob[3]), P(blob[4]), P(blob[5]), cap,
-                      P(ovf), st)
-            _lib.call("xrs_zonal_hash_accumulate", P(values_t), _dtype_code(values_t), P(zones_t),
-                      _dtype_code(zones_t), values_t.numel(), int(values_t.shape[-1]) if values_t.dim() else 1,
-                      pivot, 0 if nodata_values is None else 1,
-                      0.0 if nodata_values is None else float(nodata_values),
-                      P(keys), P(count), P(blob[2]), P(blob[3]), P(blob[4]), P(blob[5]), cap, P(ovf), st)
-        used = torch.nonzero(keys != _EMPTY_KEY).reshape(-1)
-        packed = blob[:, used].cpu().numpy()          # the only sizeable device-to-host copy (6 x zones)
-        if int(ovf.item()) == 0:
+            _lib.call("xrs_zonal_hash_run", P(values_t), _dtype_code(values_t), P(zones_t), _dtype_code(zones_t),
+                      values_t.numel(), int(values_t.shape[-1]) if values_t.dim() else 1,
+                      0 if nodata_values is None else 1, 0.0 if nodata_values is None else float(nodata_values),
+                      0 if hint is None else 1, 0.0 if hint is None else float(hint),
+                      P(keys), P(count), P(blob[2]), P(blob[3]), P(blob[4]), P(blob[5]), cap,
+                      P(packed), _MAX_OUT, P(flags), stream_ptr(values_t))
+        host = packed.cpu().numpy()                    # the one synchronising copy
+        n_used, overflow, pivot = int(host[0]), int(host[1]), float(host[2])
+        if overflow == 0:
             break
         if cap >= (1 << 24):
             raise NotImplementedError("more than 16M distinct zones are not supported")
         cap *= 16
-    k = packed[0].view(np.int64)
-    part = dict(count=packed[1].view(np.int64).copy(), s1=packed[2].copy(), s2=packed[3].copy(),
-                min=packed[4].copy(), max=packed[5].copy())
+    if n_used <= _MAX_OUT:
+        rows = host[3:].reshape(6, _MAX_OUT)[:, :n_used]
+    else:                                               # many zones: gather the used slots of the table itself
+        used = torch.nonzero(keys != _EMPTY_KEY).reshape(-1)
+        rows = blob[:, used].cpu().numpy()
+    k = np.ascontiguousarray(rows[0]).view(np.int64)
+    part = dict(count=np.ascontiguousarray(rows[1]).view(np.int64).copy(), s1=rows[2].copy(), s2=rows[3].copy(),
+                min=rows[4].copy(), max=rows[5].copy())
     if zones_t.dtype.is_floating_point:
         ids = k.view(np.float64).astype(np.float32 if zones_t.dtype == torch.float32 else np.float64)
     else:
