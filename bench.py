@@ -672,6 +672,9 @@ def run_e2e(xb, stripes, H, W, attrs, args):
     import torch
     from xrspatial_b200 import _hostmem
     _hostmem.MAX_CACHED_BYTES = max(_hostmem.MAX_CACHED_BYTES, 40 << 30)   # keep the result blocks between steps
+    # N = 1 means ONE GPU and one PCIe link, whatever else the box exposes (the numpy runners would
+    # otherwise stripe over every visible GPU)
+    os.environ["XRS_B200_DEVICES"] = str(torch.cuda.current_device())
     steps = max(1, min(args.steps, args.e2e_steps))
     eh = H
     z = None

@@ -113,6 +113,15 @@ def known_answers():
         g["zonal.result_custom_stats.%s" % k2] = np.asarray(v, dtype=np.float64)
     _, _, arr = _call(f, "result_custom_stats_dataarray")
     g["zonal.result_custom_stats_dataarray"] = np.asarray(arr)
+    # 3-D crosstab (test_zonal.py:48-58 data, :266-336 expected): values of ones, categories cat1..cat4
+    layer, zid, d = _call(f, "result_crosstab_3d")
+    g["zonal.result_crosstab_3d.layer"] = np.asarray(layer)
+    for agg, tab in d.items():
+        g["zonal.result_crosstab_3d.%s" % agg] = np.asarray([tab[k2] for k2 in ("zone", "cat1", "cat2", "cat3", "cat4")],
+                                                            dtype=np.float64)
+    nod, layer, zid, tab = _call(f, "result_nodata_values_crosstab_3d")
+    g["zonal.result_nodata_values_crosstab_3d"] = np.asarray([tab[k2] for k2 in ("zone", "cat1", "cat2", "cat3", "cat4")],
+                                                             dtype=np.float64)
     return g
 
 
@@ -287,6 +296,17 @@ def reference_outputs():
         g["crosstab.%s.table" % agg] = np.asarray(df.values, dtype=np.float64)
     df = zonal._crosstab_numpy(cz, cv, [1, 3, 9], ucats, [11.0, 13.0], 12.0, "count")
     g["crosstab.sub.table"] = np.asarray(df.values, dtype=np.float64)
+    # 3-D values (zonal.py:734-745): categories = layers, cell = statistic of the layer over the zone.
+    # A separate generator so that the arrays above keep their seeded values.
+    rng3 = np.random.default_rng(777)
+    c3 = rng3.standard_normal((4, 40, 52)).astype(np.float32) * 30 + 100
+    c3[rng3.random(c3.shape) < 0.03] = np.nan
+    c3[2, (cz == 1) & (rng3.random(cz.shape) < 0.5)] = 7.0      # nodata cells (a fully-nodata zone makes np.max raise)
+    g["crosstab3d.values"] = c3
+    cats3 = np.array([2001.0, 2002.0, 2003.0, 2004.0])
+    for agg in ("mean", "max", "min", "sum", "std", "var", "count"):
+        df = zonal._crosstab_numpy(cz, c3, [0, 1, 2, 3, 5], cats3, [2001.0, 2003.0, 2004.0], 7.0, agg)
+        g["crosstab3d.%s" % agg] = np.asarray(df.values, dtype=np.float64)
 
     # geodesic slope / aspect (geodesic.py) on a lat/lon grid near 46N, with NaNs and a flat patch
     geod = ref_loader.load("geodesic")

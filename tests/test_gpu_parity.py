@@ -972,3 +972,78 @@ def test_zonal_many_zones_and_degenerate_rasters(xb):
     assert list(one["zone"]) == [3] and one["mean"].iloc[0] == 2.5 and one["count"].iloc[0] == 1 and one["var"].iloc[0] == 0
     emp = xb.zonal_stats(da(xb, dev(np.zeros((0, 8), np.int32))), da(xb, dev(np.zeros((0, 8), np.float32))), stats_funcs=cols)
     assert len(emp) == 0 and list(emp.columns) == ["zone"] + cols
+
+
+@pytest.mark.parametrize("k", [5, 9, 15, 25])
+def test_streaming_box_convolve_many_tiles_and_sentinels(xb, k):
+    """box_stream.cu on a raster spanning several CTA tiles and row segments, with scattered NaN, +-inf
+    and a FLT_MAX-style nodata sentinel: windows holding a NaN are NaN, windows holding an infinite /
+    huge cell come back in the reference's tap order, and every OTHER window is unaffected by a bad
+    cell that passed through the running sums' neighbourhood (the round-1 summed-area table lost
+    those: ADVICE r1)."""
+    from xrspatial_b200.convolution import convolve_2d
+    rng = np.random.default_rng(1000 + k)
+    z = terrain(rng, 2100, 2304)
+    kern = np.ones((k, k)) / (k * k)
+    ref = o.convolve_2d(z, kern, nthreads=16)
+    got = convolve_2d(dev(z), kern).cpu().numpy()
+    assert used_tma(xb) == 3
+    assert_close_f32(got, ref, atol=1e-6 * 4000.0, what="box %d clean" % k)
+    d = z.copy()
+    d[rng.random(d.shape) < 0.0005] = np.nan
+    d[700, 1000] = np.inf
+    d[1500, 40] = -np.inf
+    d[300:305, 2000:2003] = np.float32(3.4028235e38)     # nodata sentinel: finite, huge
+    d[1800, 1200] = np.float32(-3.4028235e38)
+    d[40, 2303] = np.float32(1e31)
+    ref = o.convolve_2d(d, kern, nthreads=16)
+    got = convolve_2d(dev(d), kern).cpu().numpy()
+    assert used_tma(xb) == 3
+    fin = np.isfinite(ref) & (np.abs(ref) < 1e20)
+    assert_close_f32(np.where(fin, got, 0), np.where(fin, ref, 0), atol=1e-6 * 4000.0, what="box %d, ordinary windows" % k)
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
+    big = ~np.isnan(ref) & ~fin
+    assert big.any()
+    np.testing.assert_allclose(got[big], ref[big], rtol=1e-6)         # same tap order: same inf / huge values
+    # rectangular windows and a negative weight
+    for kh, kw in ((k, 3), (3, k), (1, k)):
+        kern2 = np.full((kh, kw), -0.25)
+        ref = o.convolve_2d(z[:600], kern2, nthreads=16)
+        got = convolve_2d(dev(z[:600]), kern2).cpu().numpy()
+        assert used_tma(xb) == 3
+        assert_close_f32(got, ref, atol=1e-6 * np.nanmax(np.abs(ref)), what="box %dx%d" % (kh, kw))
+
+
+def test_crosstab_3d(xb, known, refout):
+    """zonal.py:1096-1116 / :734-745: 3-D `values`, categories = coordinate of dimension `layer`, cell =
+    statistic `agg` of the layer over the zone.  The reference's own fixtures (test_zonal.py:48-58,
+    266-336) and its per-zone loop on a seeded raster."""
+    zones = known["zonal.data_zones"]
+    v3 = np.ones(4 * 3 * 8).reshape(3, 8, 4)
+    layer = int(known["zonal.result_crosstab_3d.layer"])
+    for mk in (dev, lambda a: a):
+        zagg = xb.DataArray(mk(zones), dims=("lat", "lon"))
+        vagg = xb.DataArray(mk(v3), dims=("lat", "lon", "race"))
+        vagg["race"] = ["cat1", "cat2", "cat3", "cat4"]
+        for agg in ("min", "max", "mean", "sum", "std", "var", "count"):
+            df = xb.zonal_crosstab(zagg, vagg, zone_ids=[1, 2, 3], layer=layer, agg=agg)
+            assert list(df.columns) == ["zone", "cat1", "cat2", "cat3", "cat4"]
+            np.testing.assert_allclose(np.asarray(df.values, dtype=np.float64).T, known["zonal.result_crosstab_3d." + agg],
+                                       rtol=1e-6, atol=1e-7, err_msg=agg)
+        df = xb.zonal_crosstab(zagg, vagg, zone_ids=[1, 2, 3], layer=layer, nodata_values=1)
+        np.testing.assert_array_equal(np.asarray(df.values, dtype=np.float64).T, known["zonal.result_nodata_values_crosstab_3d"])
+        with pytest.raises(ValueError, match="Invalid `layer`"):
+            xb.zonal_crosstab(zagg, vagg, layer=0)            # 'lat' carries no coordinate
+        with pytest.raises(ValueError, match="Incompatible shapes"):
+            xb.zonal_crosstab(xb.DataArray(mk(zones[:, :5]), dims=("lat", "lon")), vagg, layer=layer)
+    r = refout
+    cz, c3 = r["crosstab.zones"], r["crosstab3d.values"]
+    vagg = xb.DataArray(dev(c3), dims=("year", "y", "x"))
+    vagg["year"] = [2001.0, 2002.0, 2003.0, 2004.0]
+    zagg = xb.DataArray(dev(cz), dims=("y", "x"))
+    for agg in ("mean", "max", "min", "sum", "std", "var", "count"):
+        df = xb.zonal_crosstab(zagg, vagg, zone_ids=[0, 1, 2, 3, 5], cat_ids=[2001.0, 2003.0, 2004.0], nodata_values=7.0,
+                               agg=agg)
+        assert list(df.columns) == ["zone", 2001.0, 2003.0, 2004.0]
+        np.testing.assert_allclose(np.asarray(df.values, dtype=np.float64), r["crosstab3d." + agg], rtol=1e-5, atol=1e-4,
+                                   err_msg=agg)

@@ -98,58 +98,77 @@ def test_compass_fold_matches_the_reference_branches():
         assert min(d, 360.0 - d) <= 1e-5 * abs(ref) + 1e-4, (X, Y, got, ref)
 
 
-def _box_sat(z, kh, kw, w, th=32, tw=128, pad=16):
-    """NumPy statement of conv_box_kernel (conv.cu): per 128 x 32 tile a float64 summed-area table over
-    the tile + halo (out-of-raster cells count 0), out = w * (S[bot][right] - S[bot][left] - S[top][right]
-    + S[top][left]) + 0, NaN ring from coordinates, non-finite results recomputed tap by tap."""
+def _box_running(z, kh, kw, w, seg_rows=40):
+    """NumPy statement of box_stream_kernel (box_stream.cu): per column a float64 RUNNING sum V of the
+    last kh rows (add the entering row, emit, subtract the leaving row -- restarted every `seg_rows`
+    rows like the kernel's row segments), cells that are NaN / infinite / huge (|v| >= 2^100) kept out
+    of V and counted instead; horizontal window = difference of two inclusive prefixes of V; a window
+    holding a NaN is NaN, one holding an infinite / huge cell is re-summed tap by tap in the
+    reference's order, every other window is w * (running sum) + 0."""
     H, W = z.shape
     ry, rx = kh // 2, kw // 2
+    huge = np.float32(2.0 ** 100)
+    zp = np.full((H + 2 * ry, W + 2 * rx), np.nan, np.float32)       # TMA out-of-raster fill
+    zp[ry:ry + H, rx:rx + W] = z
+    isnan = np.isnan(zp)
+    with np.errstate(invalid="ignore"):
+        big = ~isnan & ~(np.abs(zp) < huge)
+    ordinary = np.where(isnan | big, 0.0, zp.astype(np.float64))
     out = np.empty((H, W), np.float32)
-    zz = z.astype(np.float64)
-    for y0 in range(0, H, th):
-        for x0 in range(0, W, tw):
-            gy0, gx0 = y0 - ry - 1, x0 - pad
-            sh, sw = th + kh, 160
-            tile = np.zeros((sh, sw))
-            ys, xs = np.arange(gy0, gy0 + sh), np.arange(gx0, gx0 + sw)
-            my, mx = (ys >= 0) & (ys < H), (xs >= 0) & (xs < W)
-            tile[np.ix_(my, mx)] = zz[np.ix_(ys[my], xs[mx])]
-            with np.errstate(invalid="ignore"):
-                S = np.cumsum(np.cumsum(tile, axis=0), axis=1)
-            for oy in range(min(th, H - y0)):
-                for cx in range(min(tw, W - x0)):
-                    y, x = y0 + oy, x0 + cx
-                    if y < ry or y >= H - ry or x < rx or x >= W - rx:
-                        out[y, x] = np.nan
-                        continue
-                    left, right = pad + cx - rx - 1, pad + cx + rx
-                    with np.errstate(invalid="ignore"):
-                        res = w * ((S[oy + kh, right] - S[oy + kh, left]) - (S[oy, right] - S[oy, left])) + 0.0
-                    if not np.isfinite(res):
-                        acc = 0.0
-                        with np.errstate(invalid="ignore", over="ignore"):
-                            for v in zz[y - ry:y + ry + 1, x - rx:x + rx + 1].ravel():
-                                acc = acc + w * v
-                        res = acc
-                    with np.errstate(over="ignore"):
-                        out[y, x] = np.float32(res)
+    for y0 in range(0, H, seg_rows):
+        y1 = min(y0 + seg_rows, H)
+        V = np.zeros(W + 2 * rx)
+        Cn = np.zeros(W + 2 * rx, np.int64)
+        Cb = np.zeros(W + 2 * rx, np.int64)
+        for r in range(y1 - y0 + kh - 1):
+            yy = y0 + r                        # row of the padded raster entering the window
+            V = V + ordinary[yy]
+            Cn += isnan[yy]
+            Cb += big[yy]
+            if r < kh - 1:
+                continue
+            y = y0 + r - (kh - 1)
+            P = np.concatenate([[0.0], np.cumsum(V)])
+            Pn = np.concatenate([[0], np.cumsum(Cn)])
+            Pb = np.concatenate([[0], np.cumsum(Cb)])
+            x = np.arange(W)
+            win = P[x + kw] - P[x]
+            res = (w * win + 0.0).astype(np.float32)
+            nn, nb = Pn[x + kw] - Pn[x], Pb[x + kw] - Pb[x]
+            res[nn > 0] = np.nan
+            for xx in np.nonzero((nn == 0) & (nb > 0))[0]:
+                acc = 0.0
+                with np.errstate(invalid="ignore", over="ignore"):
+                    for v in zp[y:y + kh, xx:xx + kw].astype(np.float64).ravel():
+                        acc = acc + w * v
+                    res[xx] = np.float32(acc)
+            out[y] = res
+            V = V - ordinary[y0 + r - (kh - 1)]
+            Cn -= isnan[y0 + r - (kh - 1)]
+            Cb -= big[y0 + r - (kh - 1)]
     return out
 
 
-@pytest.mark.parametrize("kh,kw", [(5, 5), (9, 9), (3, 7), (25, 3)])
-def test_summed_area_box_convolution_equals_tap_order_sums(kh, kw):
+@pytest.mark.parametrize("kh,kw", [(5, 5), (9, 9), (3, 7), (25, 3), (1, 5)])
+def test_running_box_convolution_equals_tap_order_sums(kh, kw):
+    """The running-sum form against the oracle's tap-order float64 accumulation: identical NaN masks,
+    identical +-inf / huge results, finite results to float64 rounding -- including windows next to (but
+    not containing) a FLT_MAX-style sentinel, which a summed-area table would have destroyed."""
     rng = np.random.default_rng(kh * 31 + kw)
     z = (terrain(rng, 70, 150) + 1e5).astype(np.float32)
     dirty = z.copy()
     dirty[10, 20] = np.nan
     dirty[40, 100] = np.inf
+    dirty[55, 30] = np.float32(3.4028235e38)
+    dirty[56, 31] = np.float32(-3.4028235e38)
     for w in (1.0 / (kh * kw), -0.37):
         for data in (z, dirty):
             ref = o.convolve_2d(data, np.full((kh, kw), w), nthreads=4)
-            got = _box_sat(data, kh, kw, w)
+            got = _box_running(data, kh, kw, w)
             np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
-            m = np.isfinite(ref)
-            np.testing.assert_array_equal(got[~m & ~np.isnan(ref)], ref[~m & ~np.isnan(ref)])   # +-inf cells
+            m = np.isfinite(ref) & (np.abs(ref) < 1e20)
+            odd = ~m & ~np.isnan(ref)
+            np.testing.assert_allclose(got[odd], ref[odd], rtol=1e-6)            # +-inf and huge windows
             np.testing.assert_allclose(got[m], ref[m], rtol=1e-6, atol=1e-6 * np.abs(ref[m]).max())
 
 

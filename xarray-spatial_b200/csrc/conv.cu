@@ -276,182 +276,6 @@ conv2d_fixed_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     }
 }
 
-// ----------------------------------------------------------------------------- box convolve
-// convolve_2d with a kernel whose taps are all the same weight w (np.ones((k, k)) / k**2, the
-// mean filter of the reference's docs and benchmarks): out = w * (sum of the k x k window).  The
-// window sums come from a per-tile summed-area table in float64 -- 2 adds per loaded cell and
-// 3 per output instead of k*k FMAs -- which moves the kernel from the FP64 pipe to shared-memory
-// / HBM bandwidth for every k.
-//   pass 1  column prefix sums, widening f32 -> f64 (thread per column; out-of-raster cells,
-//           which TMA delivers as NaN, count as 0: the NaN ring is set from coordinates)
-//   pass 2  row prefix sums of those (warp per row, 5 cells per lane + warp scan) -> table S
-//   pass 3  out = w * (S[bot][right] - S[bot][left] - S[top][right] + S[top][left])
-// A NaN / inf cell poisons every table entry below and to the right of it, so a non-finite
-// result is recomputed tap by tap from global memory in the generic kernel's order; finite
-// results differ from the reference's tap-order sum by f64 rounding only (~1e-13 relative to
-// the window's magnitude, against the 1e-5 parity bar of the float32 output).
-// The staging tile is free after pass 1: the next tile's TMA load overlaps passes 2 and 3.
-constexpr int kBoxCpl = 5;                 // cells per lane in the row scan
-constexpr int kBoxSW = 32 * kBoxCpl;       // table / staging row length (cells): compile-time strides
-constexpr int kBoxPad = 16;                // cells left of the tile (>= rx + 1, 64-byte aligned box start)
-constexpr int kBoxMaxK = 25;               // pad + 128 + rx <= kBoxSW and rx + 1 <= pad
-constexpr int kBoxThreads = 512;
-constexpr int kBoxTH = 32;                 // output rows per tile
-
-struct BoxGeom {
-    int H, W;      // raster (both < 2^31, checked by the caller)
-    int kh, kw, ry, rx;
-    int sh;        // table rows = kBoxTH + kh (row 0 is the row above the first window)
-    int tiles_x, tiles_y;
-    int box_h;     // rows per TMA box
-};
-
-__device__ __noinline__ float box_direct(const float *__restrict__ in, int64_t pitch_elems, int64_t y, int64_t x,
-                                         int kh, int kw, double w) {
-    double acc = 0.0;
-    const float *p = in + (y - kh / 2) * pitch_elems + (x - kw / 2);
-    for (int ky = 0; ky < kh && acc == acc; ++ky)
-        for (int kx = 0; kx < kw; ++kx) acc = fma(w, (double)p[ky * pitch_elems + kx], acc);
-    return (float)acc;
-}
-
-template <bool CHECK>
-__device__ __forceinline__ void box_column_prefix(const float *sp, double *dp, int sh, int r_lo, int r_n) {
-    double acc = 0.0;
-    int r = 0;
-    for (; r + 8 <= sh; r += 8, sp += 8 * kBoxSW, dp += 8 * kBoxSW) {
-        float v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = sp[u * kBoxSW];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const bool ok = !CHECK || (unsigned)(r + u - r_lo) < (unsigned)r_n;
-            acc += ok ? (double)v[u] : 0.0;
-            dp[u * kBoxSW] = acc;
-        }
-    }
-    for (; r < sh; ++r, sp += kBoxSW, dp += kBoxSW) {
-        const bool ok = !CHECK || (unsigned)(r - r_lo) < (unsigned)r_n;
-        acc += ok ? (double)sp[0] : 0.0;
-        dp[0] = acc;
-    }
-}
-
-__global__ void __launch_bounds__(kBoxThreads)
-conv_box_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ in, int64_t in_pitch_elems,
-                float *__restrict__ out, int64_t out_pitch_elems, const BoxGeom g, const double w) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const int nbox = (g.sh + g.box_h - 1) / g.box_h;
-    const int stage_rows = nbox * g.box_h;
-    float *stage = reinterpret_cast<float *>(smem_raw);                                  // rows of 640 B
-    double *S = reinterpret_cast<double *>(smem_raw + (size_t)stage_rows * kBoxSW * sizeof(float));
-    uint64_t *bar = reinterpret_cast<uint64_t *>(S + (size_t)g.sh * kBoxSW);
-
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tmap);
-        mbar_init(bar, 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_tiles = g.tiles_x * g.tiles_y;
-    auto issue = [&](int t) {  // thread 0 only
-        const int tile_y = t / g.tiles_x, tile_x = t - tile_y * g.tiles_x;
-        const int bx = tile_x * kTileW - kBoxPad, by = tile_y * kBoxTH - g.ry - 1;
-        mbar_arrive_expect_tx(bar, (uint32_t)(stage_rows * kBoxSW * sizeof(float)));
-        for (int b = 0; b < nbox; ++b)
-            tma_load_2d(stage + b * g.box_h * kBoxSW, &tmap, bar, bx, by + b * g.box_h);
-    };
-    if (threadIdx.x == 0 && (int)blockIdx.x < n_tiles) issue(blockIdx.x);
-
-    uint32_t parity = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int tile_y = t / g.tiles_x, tile_x = t - tile_y * g.tiles_x;
-        const int x0 = tile_x * kTileW, y0 = tile_y * kBoxTH;
-        mbar_wait(bar, parity);
-        parity ^= 1u;
-
-        // pass 1: column prefix sums (8 loads in flight per thread, one add chain per column).
-        // Table row r is raster row y0 - ry - 1 + r: rows [r_lo, r_lo + r_n) lie inside the raster;
-        // tiles whose whole table does skip the per-cell test.
-        if (threadIdx.x < kBoxSW) {
-            const int c = threadIdx.x;
-            const int gx = x0 - kBoxPad + c;
-            const int r_lo = max(0, g.ry + 1 - y0);
-            const int r_n = (gx >= 0 && gx < g.W) ? max(0, min(g.sh, g.H - (y0 - g.ry - 1)) - r_lo) : 0;
-            const bool inside = (x0 >= kBoxPad) && (x0 - kBoxPad + kBoxSW <= g.W) && (y0 > g.ry) &&
-                                (y0 - g.ry - 1 + g.sh <= g.H);  // CTA-uniform
-            if (inside) box_column_prefix<false>(stage + c, S + c, g.sh, 0, 0);
-            else box_column_prefix<true>(stage + c, S + c, g.sh, r_lo, r_n);
-        }
-        __syncthreads();
-        // the float32 staging tile is dead: fetch the next tile behind passes 2 and 3
-        if (threadIdx.x == 0 && t + (int)gridDim.x < n_tiles) issue(t + gridDim.x);
-
-        // pass 2: row prefix sums, in place; a warp scans two rows at a time so that the shuffle
-        // chains of one row hide behind the other's
-        for (int r = warp * 2; r < g.sh; r += 2 * (kBoxThreads / 32)) {
-            const bool two = r + 1 < g.sh;
-            double *row0 = S + r * kBoxSW + lane * kBoxCpl;
-            double *row1 = two ? row0 + kBoxSW : row0;
-            double e[2][kBoxCpl], inc[2];
-#pragma unroll
-            for (int j = 0; j < kBoxCpl; ++j) e[0][j] = row0[j], e[1][j] = row1[j];
-#pragma unroll
-            for (int j = 1; j < kBoxCpl; ++j) e[0][j] += e[0][j - 1], e[1][j] += e[1][j - 1];
-            inc[0] = e[0][kBoxCpl - 1];
-            inc[1] = e[1][kBoxCpl - 1];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const double u0 = __shfl_up_sync(0xffffffffu, inc[0], o);
-                const double u1 = __shfl_up_sync(0xffffffffu, inc[1], o);
-                if (lane >= o) inc[0] += u0, inc[1] += u1;
-            }
-            const double x0e = inc[0] - e[0][kBoxCpl - 1], x1e = inc[1] - e[1][kBoxCpl - 1];  // exclusive offsets
-#pragma unroll
-            for (int j = 0; j < kBoxCpl; ++j) row0[j] = e[0][j] + x0e;
-            if (two) {
-#pragma unroll
-                for (int j = 0; j < kBoxCpl; ++j) row1[j] = e[1][j] + x1e;
-            }
-        }
-        __syncthreads();
-
-        // pass 3: outputs.  Thread = (column, group of rows); the window of output row oy spans
-        // table rows oy (excluded) .. oy + kh and table columns left (excluded) .. right.
-        {
-            constexpr int kRowsPer = kBoxTH / (kBoxThreads / kTileW);
-            const int cx = threadIdx.x & (kTileW - 1), oy0 = (threadIdx.x / kTileW) * kRowsPer;
-            const int x = x0 + cx;
-            if (x < g.W) {
-                const double *top = S + oy0 * kBoxSW + (kBoxPad + cx - g.rx - 1);
-                const double *bot = top + g.kh * kBoxSW;
-                const int span = 2 * g.rx + 1;
-                double sum[kRowsPer];
-#pragma unroll
-                for (int i = 0; i < kRowsPer; ++i)
-                    sum[i] = (bot[i * kBoxSW + span] - bot[i * kBoxSW]) - (top[i * kBoxSW + span] - top[i * kBoxSW]);
-                // rows [v_lo, v_lo + v_n) of the tile are inside the raster and off the NaN ring
-                const int v_lo = max(0, g.ry - y0);
-                const int v_n = ((x >= g.rx) && (x < g.W - g.rx)) ? max(0, min(kBoxTH, g.H - g.ry - y0) - v_lo) : 0;
-                const int in_n = min(kBoxTH, g.H - y0);
-                float *op = out + (int64_t)(y0 + oy0) * out_pitch_elems + x;
-#pragma unroll
-                for (int i = 0; i < kRowsPer; ++i, op += out_pitch_elems) {
-                    const double res = w * sum[i] + 0.0;
-                    float f = (float)res;
-                    if (!((unsigned)(oy0 + i - v_lo) < (unsigned)v_n)) f = nan_of<float>();
-                    else if (!(fabs(res) <= 1.7976931348623157e308))
-                        f = box_direct(in, in_pitch_elems, y0 + oy0 + i, x, g.kh, g.kw, w);
-                    if (oy0 + i < in_n) __stcs(op, f);
-                }
-            }
-        }
-        __syncthreads();  // S is rebuilt by the next iteration
-    }
-}
-
 // Fallback for rasters TMA cannot describe: one thread per cell, bounds-checked loads.
 __global__ void __launch_bounds__(256)
 conv2d_direct_kernel(const float *__restrict__ in, int64_t in_pitch_elems, const __grid_constant__ ConvWeights cw,
@@ -827,50 +651,16 @@ static bool tile_geom(TileGeom &g, CUtensorMap *tmap, const float *in, int64_t i
     return make_tensor_map_2d(tmap, in, in_pitch, H, W, 4, g.sw, g.box_h);
 }
 
-// all taps bitwise equal (and finite), k <= 25 per side, TMA-describable raster: summed-area path
-static bool try_box(const float *in, int64_t in_pitch, float *out, int64_t out_pitch, int64_t H, int64_t W,
-                    const double *kernel, int kh, int kw, cudaStream_t s, int *rc) {
-    if (kh > kBoxMaxK || kw > kBoxMaxK) return false;
-    const double w = kernel[0];
-    if (!(fabs(w) <= 1.7976931348623157e308)) return false;
-    for (int i = 1; i < kh * kw; ++i)
-        if (memcmp(&kernel[i], &w, sizeof(double)) != 0) return false;
-    if (W % 4 != 0) return false;
-    BoxGeom g;
-    g.H = (int)H; g.W = (int)W; g.kh = kh; g.kw = kw; g.ry = kh / 2; g.rx = kw / 2;
-    g.sh = kBoxTH + kh;
-    g.tiles_x = (int)((W + kTileW - 1) / kTileW);
-    g.tiles_y = (int)((H + kBoxTH - 1) / kBoxTH);
-    if ((int64_t)g.tiles_x * g.tiles_y >= (1LL << 31)) return false;
-    g.box_h = g.sh <= 64 ? g.sh : 64;
-    static_assert(kBoxPad + kTileW + kBoxMaxK / 2 <= kBoxSW && kBoxMaxK / 2 + 1 <= kBoxPad, "box tile geometry");
-    CUtensorMap tmap;
-    if (!make_tensor_map_2d(&tmap, in, in_pitch, H, W, 4, kBoxSW, g.box_h)) return false;
-    const int nbox = (g.sh + g.box_h - 1) / g.box_h;
-    const size_t smem = (size_t)nbox * g.box_h * kBoxSW * 4 + (size_t)g.sh * kBoxSW * 8 + 16;
-    if (smem > 227 * 1024) return false;
-    *rc = XRS_OK;
-    cudaError_t e = cudaFuncSetAttribute(conv_box_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int per_sm = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_box_kernel, kBoxThreads, smem);
-    if (e != cudaSuccess) { *rc = cuda_fail(e, "conv_box_kernel setup"); return true; }
-    if (per_sm < 1) per_sm = 1;
-    int64_t grid = (int64_t)sm_count() * per_sm;
-    const int64_t n_tiles = (int64_t)g.tiles_x * g.tiles_y;
-    if (grid > n_tiles) grid = n_tiles;
-    conv_box_kernel<<<(unsigned)grid, kBoxThreads, smem, s>>>(tmap, in, in_pitch / 4, out, out_pitch / 4, g, w);
-    last_launch_info() = {3, (int)grid, kBoxThreads, (int)smem};
-    e = cudaGetLastError();
-    if (e != cudaSuccess) *rc = cuda_fail(e, "conv_box_kernel launch");
-    return true;
-}
-
 }  // namespace xrs
 
 using namespace xrs;
 
 int xrs_conv3_strip(const float *in, int64_t in_pitch, float *out, int64_t out_pitch, int64_t H, int64_t W,
                     const double *kernel, cudaStream_t s);  // surface.cu
+namespace xrs {
+bool try_box_stream(const float *in, int64_t in_pitch, float *out, int64_t out_pitch, int64_t H, int64_t W,
+                    const double *kernel, int kh, int kw, cudaStream_t s, int *rc);  // box_stream.cu
+}
 
 extern "C" {
 
@@ -882,7 +672,8 @@ int xrs_convolve2d_f32(const float *in, int64_t in_pitch, float *out, int64_t ou
     if (kh == 3 && kw == 3) return xrs_conv3_strip(in, in_pitch, out, out_pitch, H, W, kernel, (cudaStream_t)s);
     {
         int brc = XRS_OK;
-        if (try_box(in, in_pitch, out, out_pitch, H, W, kernel, kh, kw, (cudaStream_t)s, &brc)) return brc;
+        // all taps bitwise equal, k <= 25 per side, TMA-describable raster: streaming running-box kernel
+        if (try_box_stream(in, in_pitch, out, out_pitch, H, W, kernel, kh, kw, (cudaStream_t)s, &brc)) return brc;
     }
     static thread_local ConvWeights cw;
     for (int i = 0; i < kh * kw; ++i) cw.w[i] = kernel[i];

@@ -151,20 +151,51 @@ struct TileGeom {
     int n_tiles, n_segs, seg_rows;
 };
 
-template <int WARPS> struct TileShape {
+// Source element type TS of the raster in HBM (== the operator's input type for the plain kernels;
+// int16 / uint16 / int32 / float64 for direct ingestion, converted in registers with astype's
+// rounding).  The halo must keep the box start 16-byte aligned: 4 cells, 8 for 2-byte elements.
+template <typename TS> struct SrcPad { static constexpr int value = sizeof(TS) >= 4 ? 4 : 16 / (int)sizeof(TS); };
+
+template <int WARPS, int PAD = kPad> struct TileShape {
     static constexpr int kTileW = kStripW * WARPS;                       // output columns per CTA tile
-    static constexpr int kNSub = (kTileW + 2 * kPad + kSubW - 1) / kSubW;  // TMA boxes per stage
+    static constexpr int kNSub = (kTileW + 2 * PAD + kSubW - 1) / kSubW;  // TMA boxes per stage
 };
 
-template <typename Op, int ROWS, int STAGES, int WARPS>
+// 4 consecutive source cells -> operator input type
+template <typename TI, typename TS> __device__ __forceinline__ void load_cells4_as(const TS *p, TI (&c)[4]) {
+    if constexpr (sizeof(TS) == sizeof(TI) && !(TS(0.5) == TS(0))) {
+        load_cells4<TI>(reinterpret_cast<const TI *>(p), c);   // same floating type
+    } else if constexpr (sizeof(TS) == 2) {
+        const uint2 q = *reinterpret_cast<const uint2 *>(p);
+        TS e[4];
+        memcpy(e, &q, 8);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c[i] = (TI)e[i];
+    } else if constexpr (sizeof(TS) == 4) {
+        const int4 q = *reinterpret_cast<const int4 *>(p);
+        TS e[4];
+        memcpy(e, &q, 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c[i] = (TI)e[i];
+    } else {
+        const double2 q0 = *reinterpret_cast<const double2 *>(p);
+        const double2 q1 = *reinterpret_cast<const double2 *>(p + 2);
+        c[0] = (TI)q0.x; c[1] = (TI)q0.y; c[2] = (TI)q1.x; c[3] = (TI)q1.y;
+    }
+}
+
+template <typename Op, int ROWS, int STAGES, int WARPS, typename TS = typename Op::in_t>
 __global__ void __launch_bounds__((WARPS + 1) * 32)
 stencil3_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                     const __grid_constant__ typename Op::Params prm,
                     const OutPtrs<Op> outs, const TileGeom g) {
-    using T = typename Op::in_t;
+    using TI = typename Op::in_t;   // what the operator consumes
+    using T = TS;                   // what the ring holds
     using TO = typename Op::out_t;
-    constexpr int kTileW = TileShape<WARPS>::kTileW;
-    constexpr int kNSub = TileShape<WARPS>::kNSub;
+    constexpr int kPadS = SrcPad<TS>::value;
+    constexpr bool kIntegral = (TS(0.5) == TS(0));   // integer cells: the TMA unit zero-fills, NaN comes from coordinates
+    constexpr int kTileW = TileShape<WARPS, kPadS>::kTileW;
+    constexpr int kNSub = TileShape<WARPS, kPadS>::kNSub;
     constexpr int kBoxElems = ROWS * kSubW;
     constexpr int kStageElems = kNSub * kBoxElems;
     constexpr uint32_t kStageBytes = kStageElems * sizeof(T);
@@ -199,7 +230,7 @@ stencil3_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                 const int64_t y0 = (int64_t)seg * g.seg_rows;
                 const int64_t y1 = min(y0 + (int64_t)g.seg_rows, g.H);
                 const int n_chunks = ((int)(y1 - y0) + 2 + ROWS - 1) / ROWS;  // input rows y0-1 .. y1
-                const int bx = tile * kTileW - kPad, by = (int)y0 - 1;
+                const int bx = tile * kTileW - kPadS, by = (int)y0 - 1;
                 for (int c = 0; c < n_chunks; ++c) {
                     // a fresh barrier passes a wait on parity 1: the first lap never blocks
                     mbar_wait(&empty[stage], ((phase >> stage) & 1u) ^ 1u);
@@ -217,7 +248,7 @@ stencil3_tma_kernel(const __grid_constant__ CUtensorMap tmap,
     }
 
     // ---- consumers.  Column cc of the stage (0 = first halo cell) lives in box cc / kSubW.
-    const int cc = kPad + kStripW * warp + kLaneCells * lane;
+    const int cc = kPadS + kStripW * warp + kLaneCells * lane;
     const int off_c = (cc / kSubW) * kBoxElems + cc % kSubW;
     const int off_l = ((cc - 1) / kSubW) * kBoxElems + (cc - 1) % kSubW;
     const int off_r = ((cc + kLaneCells) / kSubW) * kBoxElems + (cc + kLaneCells) % kSubW;
@@ -233,6 +264,7 @@ stencil3_tma_kernel(const __grid_constant__ CUtensorMap tmap,
         Op op(prm);
         const int64_t xl = (int64_t)tile * kTileW + kStripW * warp + kLaneCells * lane;
         const bool lane_ok = xl < g.W;  // W % 4 == 0 on this path: a lane is all-in or all-out
+        const bool left_oob = xl == 0, right_oob = xl + 4 >= g.W;   // integer sources only
         // output pointers one row above the first emitted row (y0 - 2): advanced before every store
         TO *optr[Op::kOutputs];
 #pragma unroll
@@ -243,16 +275,24 @@ stencil3_tma_kernel(const __grid_constant__ CUtensorMap tmap,
             phase ^= (1u << stage);
             const T *buf = ring + stage * kStageElems;
             const int rel = c * ROWS - 2;  // output row (relative to y0) of the stage's first row
+            const int64_t ybase = y0 - 1 + (int64_t)c * ROWS;
             // Straight-line over the ROWS rows of the stage (no branch around the operator state
             // update, so the rolling registers are renamed, not moved).  Rows whose output row
             // falls outside [y0, y1) -- the two lead-in rows and the tail of the last chunk --
             // still update the state; only their store is predicated off.
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
-                Row6<T> row;
-                load_cells4(buf + off_c + r * kSubW, row.c);
-                row.l = buf[off_l + r * kSubW];
-                row.r = buf[off_r + r * kSubW];
+                Row6<TI> row;
+                load_cells4_as<TI, TS>(buf + off_c + r * kSubW, row.c);
+                row.l = (TI)buf[off_l + r * kSubW];
+                row.r = (TI)buf[off_r + r * kSubW];
+                if constexpr (kIntegral) {
+                    const int64_t y = ybase + r;
+                    const bool row_oob = (y < 0) || (y >= g.H);
+                    if (row_oob || left_oob) row.l = nan_of<TI>();
+                    if (row_oob || right_oob) row.r = nan_of<TI>();
+                    if (row_oob || !lane_ok) row.c[0] = row.c[1] = row.c[2] = row.c[3] = nan_of<TI>();
+                }
                 Vec4<TO> o[Op::kOutputs];
                 op.step(row, o);
                 const bool st = lane_ok && (unsigned)(rel + r) < (unsigned)seg_h;
@@ -411,6 +451,25 @@ stencil3_cpasync_kernel(const typename Op::in_t *__restrict__ in, int64_t in_pit
 }
 
 // ----------------------------------------------------------------------------- host launcher
+// Row segments: ~8 tasks per resident CTA, but segments of >= 32 rows so the 2 halo rows re-read per
+// segment stay a small overhead; a multiple of ROWS (minus the 2 lead-in rows) so the last chunk of a
+// segment wastes < ROWS rows.
+inline TileGeom make_tile_geom(int64_t H, int64_t W, int tile_w, int rows, int64_t resident_ctas) {
+    TileGeom g;
+    g.H = H;
+    g.W = W;
+    g.n_tiles = (int)((W + tile_w - 1) / tile_w);
+    int64_t want_segs = (resident_ctas * 8 + g.n_tiles - 1) / g.n_tiles;
+    int64_t seg_rows = (H + want_segs - 1) / (want_segs > 0 ? want_segs : 1);
+    if (seg_rows < 32) seg_rows = 32;
+    if (seg_rows > H) seg_rows = H;
+    seg_rows = ((seg_rows + 2 + rows - 1) / rows) * rows - 2;
+    if (seg_rows < 1) seg_rows = 1;
+    g.seg_rows = (int)seg_rows;
+    g.n_segs = (int)((H + seg_rows - 1) / seg_rows);
+    return g;
+}
+
 // ROWS x STAGES = the TMA ring of the CTA-wide pipeline, WARPS consumer warps per CTA, CTAS CTAs per
 // SM: tuned per operator on B200 (scripts/tune/, profiles/r02_tune*.txt) -- ~65 KB in flight per SM
 // for the light operators, more warps and a deeper ring for the arithmetic-heavy ones.
@@ -460,22 +519,8 @@ int launch_stencil3(const typename Op::in_t *in, int64_t in_pitch_bytes, const t
         XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (WARPS + 1) * 32, smem));
         if (per_sm < 1) per_sm = 1;
         if (per_sm > CTAS) per_sm = CTAS;
-        TileGeom g;
-        g.H = H;
-        g.W = W;
-        g.n_tiles = (int)((W + kTileW - 1) / kTileW);
-        // Row segments: ~8 tasks per resident CTA, but segments of >= 32 rows so the 2 halo rows
-        // re-read per segment stay a small overhead; a multiple of ROWS (minus the 2 lead-in rows)
-        // so the last chunk of a segment wastes < ROWS rows.
         const int64_t resident = (int64_t)sms * per_sm;
-        int64_t want_segs = (resident * 8 + g.n_tiles - 1) / g.n_tiles;
-        int64_t seg_rows = (H + want_segs - 1) / (want_segs > 0 ? want_segs : 1);
-        if (seg_rows < 32) seg_rows = 32;
-        if (seg_rows > H) seg_rows = H;
-        seg_rows = ((seg_rows + 2 + ROWS - 1) / ROWS) * ROWS - 2;
-        if (seg_rows < 1) seg_rows = 1;
-        g.seg_rows = (int)seg_rows;
-        g.n_segs = (int)((H + seg_rows - 1) / seg_rows);
+        const TileGeom g = make_tile_geom(H, W, kTileW, ROWS, resident);
         const int64_t n_tasks = (int64_t)g.n_tiles * g.n_segs;
         int64_t grid = resident < n_tasks ? resident : n_tasks;
         li.used_tma = 1;

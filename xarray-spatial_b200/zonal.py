@@ -599,10 +599,74 @@ def _pivot_pairs(sel, cats, pz, pv, pc):
     return total, counts
 
 
+def _crosstab_3d(zones, values, zone_ids, cat_ids, layer, agg, nodata_values, comm):
+    """3-D `values` (zonal.py:1096-1116, `_single_zone_crosstab_3d` :734-745): the categories are the
+    coordinate values of dimension `layer`, and cell (zone, category) is statistic `agg` of that
+    category's 2-D layer over the zone -- i.e. one zonal.stats pass per selected layer."""
+    import torch
+    if agg not in _DEFAULT_STATS:
+        raise ValueError("`agg` method for 3D numpy backed data array must be one of following %s"
+                         % (list(_DEFAULT_STATS),))
+    if layer is None:
+        layer = 0
+    try:
+        ldim = values.dims[layer]
+        if ldim not in values.coords:
+            raise KeyError(ldim)
+        unique_cats = np.asarray(getattr(values.coords[ldim], "values", values.coords[ldim]))
+    except (IndexError, KeyError, TypeError):
+        raise ValueError("Invalid `layer`")
+    axis = list(values.dims).index(ldim)
+    host = isinstance(values.data, np.ndarray)
+    vt = torch.from_numpy(np.ascontiguousarray(values.data)).cuda() if host else as_device_tensor(values.data)
+    zt = torch.from_numpy(np.ascontiguousarray(zones.data)).cuda() if isinstance(zones.data, np.ndarray) \
+        else as_device_tensor(zones.data)
+    vt = torch.movedim(vt, axis, 0)
+    if tuple(zt.shape) != tuple(vt.shape[1:]):
+        raise ValueError("Incompatible shapes")
+    zt = _prepare(zt, (torch.int32, torch.int64, torch.float32, torch.float64))
+    if cat_ids is None:
+        cats = list(unique_cats.tolist())
+    else:
+        cats = [c for c in cat_ids if c in unique_cats]
+    cat_pos = {c: j for j, c in enumerate(unique_cats.tolist())}
+    zf = zt.reshape(-1)
+    zfin = zf[torch.isfinite(zf)] if zf.dtype.is_floating_point else zf
+    unique_zones = torch.unique(zfin).cpu().numpy()
+    if zone_ids is None:
+        sel = unique_zones
+    else:
+        sel = np.array([z for z in zone_ids if z in unique_zones], dtype=unique_zones.dtype)
+    d = {"zone": sel}
+    for c in cats:
+        lt = vt[cat_pos[c]].contiguous()
+        lt = lt if lt.dtype in (torch.float32, torch.float64) else lt.to(torch.float64)
+        ids, part, pivot0 = hash_partials(zt, lt, nodata_values, comm=comm)
+        pos = np.searchsorted(ids, sel)
+        pos = np.clip(pos, 0, max(len(ids) - 1, 0))
+        hit = (ids[pos] == sel) if len(ids) else np.zeros(len(sel), bool)
+        if agg == "majority":
+            col_all = majority_by_zone(zt, lt, ids, nodata_values, comm=comm)
+        elif agg in ("std", "var") and lt.dtype == torch.float64 and len(ids):
+            cnt = part["count"].astype(np.float64)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                means = np.where(cnt > 0, pivot0 + part["s1"] / cnt, 0.0)
+            part2, piv2 = zonal_partials(zt, lt, ids, nodata_values, pivot=means, comm=comm)
+            col_all = finalize(part2, piv2, [agg])[agg]
+        else:
+            col_all = finalize(part, np.full(len(ids), pivot0), [agg])[agg]
+        col = np.where(hit, col_all[pos] if len(ids) else np.nan, np.nan)
+        if agg == "count":          # np.ma.count of an empty selection is 0, and the column is integer
+            col = np.where(np.isnan(col), 0, col).astype(np.int64)
+        d[c] = col
+    return pd.DataFrame(d)
+
+
 def crosstab(zones, values, zone_ids=None, cat_ids=None, layer=None, agg="count", nodata_values=None, comm=None):
-    """Cross-tabulated cell counts (or percentages) of the categories of a 2-D `values` raster
-    per zone (zonal.py:922-1155, 2-D case): DataFrame with a `zone` column and one column per
-    category.  Built on the (zone, value) pair histogram of xrs_zonal_pair_count."""
+    """Cross-tabulation of a `values` raster by zone (zonal.py:922-1155): a `zone` column and one column
+    per category.  2-D values: cell counts (or percentages) of the categorical values per zone, built on
+    the (zone, value) pair histogram of xrs_zonal_pair_count.  3-D values: statistic `agg` of every
+    category layer per zone (`layer` names the category dimension)."""
     if not isinstance(zones, DataArray):
         raise TypeError("zones must be instance of DataArray")
     if not isinstance(values, DataArray):
@@ -612,7 +676,7 @@ def crosstab(zones, values, zone_ids=None, cat_ids=None, layer=None, agg="count"
     if values.ndim not in (2, 3):
         raise ValueError("`values` must use either 2D or 3D coordinates.")
     if values.ndim == 3:
-        raise NotImplementedError("3-D `values` are not supported by the B200 backend")
+        return _crosstab_3d(zones, values, zone_ids, cat_ids, layer, agg, nodata_values, comm)
     validate_arrays(zones, values)
     if agg not in ("percentage", "count"):
         raise ValueError("`agg` method for 2D data array must be one of following ['percentage', 'count']")
