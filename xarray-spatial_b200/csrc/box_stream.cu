@@ -2,10 +2,11 @@
 // (np.ones((k, k)) / k**2: the mean filter of the reference's docs and of benchmarks/; also any
 // rectangular kh x kw): out = w * (sum of the window), reference convolution.py:285-313.
 //
-// A separable RUNNING box on the CTA-wide TMA pipeline of stencil3.cuh, HBM-bound for every k
+// A separable RUNNING box on the CTA-wide TMA pipeline of stencil3.cuh: O(1) work per cell for every k
 // (the round-1 kernel built a summed-area table per tile in shared memory and was bound by
-// shared-memory bandwidth at 0.27-0.33 of the HBM roofline):
-//   * one producer warp streams the tile's rows (one row per stage, 256-cell TMA boxes, NaN
+// shared-memory bandwidth at 0.27-0.33 of the HBM roofline; this one reaches 0.31-0.43 on B200 and is
+// bound by the latency of its float64 shuffle / add chains):
+//   * one producer warp streams the tile's rows (one row per stage, 224-cell TMA boxes, NaN
 //     out-of-raster fill) into a ring of kh + 1 + PREFETCH row slots; consumer warps march down;
 //   * vertical: every lane keeps the running column sums V of its 4 columns over the last kh rows
 //     in float64 registers:  V += row(y + ry)  ...emit row y...  V -= row(y - ry)   (the row that
