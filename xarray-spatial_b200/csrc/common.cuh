@@ -191,10 +191,21 @@ struct CompassPre {
     float ts, K;
     bool flat;
 };
+// NaN-propagating max / min (FMNMX.NAN): a NaN operand gives NaN, unlike fmaxf / fminf
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float min_nan(float a, float b) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
 __device__ __forceinline__ CompassPre compass_pre(float u, float v) {
     const float au = fabsf(u), av = fabsf(v);
     const bool swap = au > av;                // closer to the +-u axis (east / west)
-    const float mx = swap ? au : av, mn = swap ? av : au;
+    const float mx = max_nan(au, av), mn = min_nan(au, av);   // a NaN sum makes both NaN
     const float t = mn * rcp_approx(mx);
     // sigma = sign(u) * sign(v), negated in the swapped octants: flip t's sign bit
     const unsigned sgn = ((__float_as_uint(u) ^ __float_as_uint(v)) & 0x80000000u) ^ (swap ? 0x80000000u : 0u);
@@ -203,7 +214,7 @@ __device__ __forceinline__ CompassPre compass_pre(float u, float v) {
     const float k_ns = (v > 0.0f) ? ((u < 0.0f) ? 360.0f : 0.0f) : 180.0f;
     const float k_ew = (u > 0.0f) ? 90.0f : 270.0f;
     c.K = swap ? k_ew : k_ns;
-    c.flat = (au == 0.0f) && (av == 0.0f);
+    c.flat = mx == 0.0f;                       // false for NaN: atan2(0, NaN) is NaN in the reference, not "flat"
     return c;
 }
 __device__ __forceinline__ float compass_deg(float u, float v) {
