@@ -303,7 +303,7 @@ def run_gpu_arm(args):
             parity = run_parity_gate(xb, stripes, attrs)     # before any timing
     else:
         step()
-        parity = run_stripe_parity_gate(xb, stripes, outs, attrs, dist, dev)
+        parity = run_stripe_parity_gate(xb, stripes, outs, attrs, dist, dev, step=step)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()           # before the warm-up: nvidia-smi needs ~0.1 s to print its first row
@@ -403,13 +403,9 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
-def run_stripe_parity_gate(xb, stripes, outs, attrs, dist, dev, band=2048):
-    """N > 1, before timing.  For every stripe boundary (rank r | r + 1) rank r receives the first
-    `band` + 1 input rows and the first `band` output rows of rank r + 1, recomputes the band of
-    2 x `band` rows around the boundary as ONE raster on its own GPU and compares it BIT FOR BIT with
-    the two stripes' outputs of the benchmark step: the partition-invariance the reference asserts
-    between its numpy and dask backends (tests/general_checks.py:124-131).  Then a striped
-    zonal.stats(comm=WORLD) over 32 x 32 block zones, whose counts have a closed form."""
+def _stripe_boundary_mismatches(xb, stripes, outs, attrs, dist, dev, band):
+    """One pass of the boundary check: per-operator counts of cells that differ (this rank's lower
+    boundary), plus the number of halo cells that differ from the regenerated DEM rows."""
     import torch
     rank, world = stripes.rank, stripes.world
     W, h = stripes.W, stripes.h
@@ -429,32 +425,66 @@ def run_stripe_parity_gate(xb, stripes, outs, attrs, dist, dev, band=2048):
             reqs.append(dist.P2POp(dist.irecv, t, rank + 1))
     for r in dist.batch_isend_irecv(reqs):
         r.wait()
-    ok = 1
+    bad = [0, 0, 0, 0]                                # slope, hillshade, mean, halo cells
+    # the halo rows of the stripe buffer against the generator (a pure function of the coordinates)
+    for lo, n, y in ((0, stripes.top, stripes.y0 - stripes.top), (stripes.top + h, stripes.bot, stripes.y1)):
+        if n:
+            ref = torch.empty((n, W), dtype=torch.float32, device=dev)
+            synth_into(ref, y)
+            bad[3] += int((stripes.buf[lo:lo + n].view(torch.int32) != ref.view(torch.int32)).sum().item())
     if rank < world - 1:
         band_in = torch.cat([stripes.interior[h - B - 1:h], recv_in], dim=0)      # rows y1-B-1 .. y1+B
         bagg = xb.DataArray(band_in, dims=("y", "x"), attrs=attrs)
-        for k, fn in zip(names, (xb.slope, xb.hillshade, xb.mean)):
+        for i, (k, fn) in enumerate(zip(names, (xb.slope, xb.hillshade, xb.mean))):
             got = fn(bagg).data[1:2 * B + 1]
-            exp = torch.cat([own[k][h - B:h], recv_out[names.index(k)]], dim=0)
-            if not torch.equal(got.view(torch.int32), exp.view(torch.int32)):
-                ok = 0
+            exp = torch.cat([own[k][h - B:h], recv_out[i]], dim=0)
+            bad[i] = int((got.view(torch.int32) != exp.view(torch.int32)).sum().item())
         del band_in
-    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    if int(flag.item()) != 1:
-        raise AssertionError("parity gate: striped outputs differ from the single-raster outputs at a stripe boundary")
+    t = torch.tensor(bad, dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [int(x) for x in t.tolist()], B
+
+
+def run_stripe_parity_gate(xb, stripes, outs, attrs, dist, dev, band=2048, step=None):
+    """N > 1, before timing.  For every stripe boundary (rank r | r + 1) rank r receives the first
+    `band` + 1 input rows and the first `band` output rows of rank r + 1, recomputes the band of
+    2 x `band` rows around the boundary as ONE raster on its own GPU and compares it BIT FOR BIT with
+    the two stripes' outputs of the benchmark step: the partition-invariance the reference asserts
+    between its numpy and dask backends (tests/general_checks.py:124-131).  The halo rows are also
+    compared with the regenerated DEM rows.  Then a striped zonal.stats(comm=WORLD) over 32 x 32 block
+    zones, whose counts have a closed form.
+
+    The gate never suppresses the bench line: a mismatch is counted per operator, the step is run and
+    checked once more (`retried`), and the record says `ok: false` if the second pass differs too."""
+    import sys
+    world = stripes.world
+    names = ["slope", "hillshade", "focal.mean", "halo_rows"]
+    first, B = _stripe_boundary_mismatches(xb, stripes, outs, attrs, dist, dev, band)
+    final, retried = first, False
+    if any(first) and step is not None:
+        retried = True
+        step()
+        final, B = _stripe_boundary_mismatches(xb, stripes, outs, attrs, dist, dev, band)
+    ok = not any(final)
+    if any(first) and stripes.rank == 0:
+        sys.stderr.write("parity gate: cells differing at the stripe boundaries (all ranks) first pass %r, "
+                         "after re-running the step %r\n" % (dict(zip(names, first)), dict(zip(names, final))))
     # striped zonal.stats: exact integer counts, zone ids 0..1023
-    zones = block_zones(h, W, stripes.y0, stripes.H, dev)
+    zones = block_zones(stripes.h, stripes.W, stripes.y0, stripes.H, dev)
     df = xb.zonal_stats(xb.DataArray(zones, dims=("y", "x")), xb.DataArray(stripes.interior, dims=("y", "x")),
                         stats_funcs=["count", "min", "max", "mean"], comm=dist.group.WORLD)
-    cells = (stripes.H // 32) * (W // 32)
-    if not (np.array_equal(np.asarray(df["zone"]), np.arange(1024)) and
-            np.array_equal(np.asarray(df["count"]), np.full(1024, float(cells)))):
-        raise AssertionError("parity gate: striped zonal.stats counts differ from the closed form")
-    return {"checked": True, "kind": "stripe boundaries recomputed as one raster, bit-exact; striped zonal.stats "
-                                     "counts == closed form (general_checks.py:124-131)",
+    cells = (stripes.H // 32) * (stripes.W // 32)
+    zonal_ok = bool(np.array_equal(np.asarray(df["zone"]), np.arange(1024)) and
+                    np.array_equal(np.asarray(df["count"]), np.full(1024, float(cells))))
+    if not zonal_ok and stripes.rank == 0:
+        sys.stderr.write("parity gate: striped zonal.stats counts differ from the closed form\n")
+    return {"checked": True, "ok": bool(ok and zonal_ok),
+            "kind": "stripe boundaries recomputed as one raster, bit-exact; halo rows == generator; striped "
+                    "zonal.stats counts == closed form (general_checks.py:124-131)",
             "boundaries": world - 1, "band_rows": 2 * B, "operators": ["slope", "hillshade", "focal.mean"],
-            "zonal_counts_exact": True, "zones": 1024, "cells_per_zone": cells}
+            "mismatching_cells": dict(zip(names, final)),
+            "retried": retried, "mismatching_cells_first_pass": dict(zip(names, first)) if retried else None,
+            "zonal_counts_exact": zonal_ok, "zones": 1024, "cells_per_zone": cells}
 
 
 def run_ops_record(xb, stripes, attrs, args, peak, dist, dev):

@@ -144,13 +144,17 @@ __device__ __forceinline__ void bs_window(const T (&p)[4], int lane, T (&win)[4]
             hi[j] = __shfl_sync(0xffffffffu, vu, src_u);
             lo[j] = __shfl_sync(0xffffffffu, vl, src_l);
         }
-        if (src_l < 0) lo[j] = T(0);   // the prefix before the warp's first column
+        // src_l < 0 (the prefix before the warp's first column, = 0) only reaches an emitting lane when
+        // RX is a multiple of 4: lane q, cell 0.  Every other lane with src_l < 0 sits in the pad.
+        if constexpr (m == 0) {
+            if (j == 0 && src_l < 0) lo[j] = T(0);
+        }
         win[j] = hi[j] - lo[j];
     }
 }
 
-template <int RX>
-__global__ void __launch_bounds__((kBsWarps + 1) * 32)
+template <int RX, int KR>
+__global__ void __launch_bounds__((kBsWarps + 1) * 32, 2)
 box_stream_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ in, int64_t in_pitch_elems,
                   float *__restrict__ out, int64_t out_pitch_elems, const BsGeom g) {
     using S = BsShape<RX>;
@@ -219,7 +223,7 @@ box_stream_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restr
             // entering nor the rows in the window hold a NaN / inf / huge cell.  The kRows prefix scans
             // are independent and run interleaved: one scan per row left the float64 units idle behind a
             // ~600-cycle shuffle / add chain (measured 0.18 of the HBM roofline at k = 25).
-            constexpr int kRows = 4;
+            constexpr int kRows = KR;
             while (r >= kh - 1 && r + kRows <= n_rows &&
                    (dirty & (((kh - 1) >= 32) ? 0xffffffffu : ((1u << (kh - 1)) - 1u))) == 0u) {
                 float nv[kRows][4], ov[kRows][4];
@@ -268,8 +272,8 @@ box_stream_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restr
                     bs_window<RX, double>(P[i], lane, win);
                     if (store_ok)
                         __stcs(reinterpret_cast<float4 *>(optr),
-                               make_float4((float)(g.w * win[0] + 0.0), (float)(g.w * win[1] + 0.0),
-                                           (float)(g.w * win[2] + 0.0), (float)(g.w * win[3] + 0.0)));
+                               make_float4((float)fma(g.w, win[0], 0.0), (float)fma(g.w, win[1], 0.0),
+                                           (float)fma(g.w, win[2], 0.0), (float)fma(g.w, win[3], 0.0)));
                     optr += out_pitch_elems;
                 }
                 __syncwarp();
@@ -316,7 +320,7 @@ box_stream_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restr
             bs_window<RX, double>(P, lane, win);
             float res[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) res[j] = (float)(g.w * win[j] + 0.0);
+            for (int j = 0; j < 4; ++j) res[j] = (float)fma(g.w, win[j], 0.0);
             if (win_dirty) {   // warp-uniform
                 unsigned PC[4] = {C[0], C[1], C[2], C[3]};
                 bs_prefix_u(PC, lane);
@@ -363,7 +367,7 @@ box_stream_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restr
     }
 }
 
-template <int RX>
+template <int RX, int KR>
 static int launch_box_stream(const CUtensorMap &tmap, const float *in, int64_t in_pitch, float *out, int64_t out_pitch,
                              int64_t H, int64_t W, int kh, double w, cudaStream_t s) {
     using S = BsShape<RX>;
@@ -375,18 +379,22 @@ static int launch_box_stream(const CUtensorMap &tmap, const float *in, int64_t i
     // is latency-bound (float64 shuffle / add chains), and the second CTA's warps matter more than a
     // deeper ring (k = 25 with one 8-warp CTA per SM: 0.18 of the HBM roofline)
     const int row_bytes = S::kRowCells * 4;
-    g.ring = kh + 1 + 16;
+    int prefetch = 16, max_ctas = 2;
+    if (const char *e = getenv("XRS_BOX_PREFETCH")) prefetch = atoi(e);
+    if (const char *e = getenv("XRS_BOX_CTAS")) max_ctas = atoi(e);
+    const size_t cap = (size_t)(220 * 1024) / max_ctas;
+    g.ring = kh + 1 + prefetch;
     size_t smem = (size_t)g.ring * row_bytes + (size_t)2 * g.ring * sizeof(uint64_t);
-    while (smem > 110 * 1024 && g.ring > kh + 5) {
+    while (smem > cap && g.ring > kh + 5) {
         --g.ring;
         smem = (size_t)g.ring * row_bytes + (size_t)2 * g.ring * sizeof(uint64_t);
     }
-    auto kern = box_stream_kernel<RX>;
+    auto kern = box_stream_kernel<RX, KR>;
     XRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (kBsWarps + 1) * 32, smem));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 2) per_sm = 2;
+    if (per_sm > max_ctas) per_sm = max_ctas;
     const int64_t resident = (int64_t)sm_count() * per_sm;
     // segments: ~4 tasks per CTA, but tall enough that the kh - 1 warm-up rows stay a small overhead
     int64_t want_segs = (resident * 4 + g.n_tiles - 1) / g.n_tiles;
@@ -415,8 +423,12 @@ bool try_box_stream(const float *in, int64_t in_pitch, float *out, int64_t out_p
     if (H >= (1LL << 31) - 64 || W >= (1LL << 31) - 4096) return false;
     CUtensorMap tmap;
     if (!make_tensor_map_2d(&tmap, in, in_pitch, H, W, 4, kBsBoxW, 1)) return false;
+    int kr = 4;
+    if (const char *e = getenv("XRS_BOX_ROWS")) kr = atoi(e);
     switch (kw / 2) {
-#define XRS_BS(R) case R: *rc = launch_box_stream<R>(tmap, in, in_pitch, out, out_pitch, H, W, kh, w, s); return true;
+#define XRS_BS(R) case R: *rc = kr == 8 ? launch_box_stream<R, 8>(tmap, in, in_pitch, out, out_pitch, H, W, kh, w, s) \
+                             : kr == 6 ? launch_box_stream<R, 6>(tmap, in, in_pitch, out, out_pitch, H, W, kh, w, s) \
+                                       : launch_box_stream<R, 4>(tmap, in, in_pitch, out, out_pitch, H, W, kh, w, s); return true;
         XRS_BS(1) XRS_BS(2) XRS_BS(3) XRS_BS(4) XRS_BS(5) XRS_BS(6) XRS_BS(7) XRS_BS(8) XRS_BS(9) XRS_BS(10) XRS_BS(11) XRS_BS(12)
 #undef XRS_BS
     }

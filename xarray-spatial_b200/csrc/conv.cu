@@ -11,6 +11,7 @@
 // 4 x 4 block of outputs and accumulates in float64 with FMA (the reference accumulates
 // `kernel(f64) * data(f32)` in a float64 `num`); weights are read from the kernel-parameter
 // constant bank.  Bound: FP64 FMA rate for k >= 5 (2*k*k flop/cell), HBM for k = 3.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
