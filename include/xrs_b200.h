@@ -224,6 +224,17 @@ int xrs_zonal_hash_run(const void *values, int values_dtype, const void *zones, 
                        int64_t *keys, int64_t *count, double *s1, double *s2, double *vmin, double *vmax, int cap,
                        double *packed, int max_out, int *flags, xrs_stream_t s);
 
+/* Second pass for float64 rasters (numpy's two-pass variance, zonal.py:75-76 `ndarray.std / var`): the same
+ * streaming group-by over the table xrs_zonal_hash_run left behind -- `keys` as populated by the first pass,
+ * read only -- with sums taken about `zone_pivots[slot]` (device, `cap` doubles: the zone's mean from the
+ * first pass) instead of one global pivot, so that s2 / n - (s1 / n)^2 does not cancel.  count / s1 / s2 /
+ * vmin / vmax: a second set of `cap`-entry accumulators (reset here); `packed` / `flags` as above
+ * (packed[2] = 0).  Replaces the round-1 lookup-table kernel (xrs_zonal_partials_ex) on this path. */
+int xrs_zonal_hash_second_pass(const void *values, int values_dtype, const void *zones, int zones_dtype, int64_t n,
+                               int64_t row_len, int has_nodata, double nodata, const int64_t *keys,
+                               const double *zone_pivots, int64_t *count, double *s1, double *s2, double *vmin,
+                               double *vmax, int cap, double *packed, int max_out, int *flags, xrs_stream_t s);
+
 /* `majority` (zonal.py:56-68): counts (zone, value) pairs of float32 values / int32 zones into
  * a hash table (keys/count of `cap` entries, initialised with xrs_zonal_hash_init; key =
  * (zone << 32) | float32 bits of the value, -0.0 folded into +0.0).  The caller picks the most

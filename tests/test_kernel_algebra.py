@@ -172,6 +172,81 @@ def test_running_box_convolution_equals_tap_order_sums(kh, kw):
             np.testing.assert_allclose(got[m], ref[m], rtol=1e-6, atol=1e-6 * np.abs(ref[m]).max())
 
 
+def _lane_sum_windows(v, rx):
+    """NumPy statement of bs_lanesum / bs_cell (box_stream.cu, second-generation kernel): v[lane, j] = the
+    float64 column sums a warp's 32 lanes hold (4 columns each).  Every lane forms the inclusive prefix
+    and suffix of its own four values; the window of column 4 l + j is suffix[.] of the lane its left end
+    falls in + prefix[.] of the lane its right end falls in + the totals of the whole lanes in between,
+    every operand at a fixed lane distance (warp shuffles: a lane past the warp's end reads itself)."""
+    q, m = divmod(rx, 4)
+    lanes = np.arange(32)
+
+    def frm(x, d):                       # __shfl_down_sync / __shfl_up_sync semantics
+        src = lanes + d
+        src = np.where((src < 0) | (src > 31), lanes, src)
+        return x[src]
+
+    pre = np.cumsum(v, axis=1)
+    suf = np.empty_like(v)
+    suf[:, 3] = v[:, 3]
+    suf[:, 2] = v[:, 2] + suf[:, 3]
+    suf[:, 1] = v[:, 1] + suf[:, 2]
+    suf[:, 0] = pre[:, 3]
+    tot = pre[:, 3]
+    core, tl, tr = tot, np.zeros(32), np.zeros(32)
+    if q == 2:
+        core = (frm(tot, -1) + tot) + frm(tot, 1)
+    if q == 3:
+        pair = tot + frm(tot, 1)
+        core = (frm(pair, -2) + pair) + frm(tot, 2)
+    if q >= 1 and m > 0:
+        tl, tr = frm(tot, -q), frm(tot, q)
+    win = np.empty_like(v)
+    for j in range(4):
+        a, b = j - m, j + m
+        if q == 0 and a >= 0 and b <= 3:
+            assert a == 0 or b == 3
+            win[:, j] = pre[:, b] if a == 0 else suf[:, a]
+            continue
+        dl, ia = -q - (1 if a < 0 else 0), (a + 4) & 3
+        dh, ib = q + (1 if b >= 4 else 0), b & 3
+        ends = frm(suf[:, ia], dl) + frm(pre[:, ib], dh)
+        if q == 0:
+            win[:, j] = ends + tot if (a < 0 and b >= 4) else ends
+        else:
+            full = core
+            if a < 0:
+                full = full + tl
+            if b >= 4:
+                full = full + tr
+            win[:, j] = ends + full
+    return win
+
+
+@pytest.mark.parametrize("rx", range(1, 13))
+def test_lane_sum_windows_equal_direct_window_sums(rx):
+    """The shuffle algebra of the second-generation running-box kernel: for every lane that emits
+    (4 * lane in [pad, 128 - pad), pad = rx rounded up to a multiple of 4) the lane-sum window equals the
+    direct sum of the 2 rx + 1 columns (integers: exact in any order), and a NaN column (beyond the
+    raster's edge: TMA fill) reaches exactly the windows that contain it -- no masking needed."""
+    rng = np.random.default_rng(rx)
+    cols = rng.integers(-1000, 1000, 128).astype(np.float64)
+    pad = (rx + 3) // 4 * 4
+    for nan_cols in ((), range(0, pad), range(128 - pad, 128), (pad + rx,)):
+        c = cols.copy()
+        c[list(nan_cols)] = np.nan
+        with np.errstate(invalid="ignore"):
+            win = _lane_sum_windows(c.reshape(32, 4), rx).reshape(128)
+        x = np.arange(pad, 128 - pad)
+        direct = np.array([c[i - rx:i + rx + 1].sum() for i in x])
+        np.testing.assert_array_equal(win[x], direct)        # NaN == NaN positions included
+    # the packed 16-bit pair counts go through the same algebra with unsigned adds
+    cnt = rng.integers(0, 3, 128).astype(np.float64)
+    win = _lane_sum_windows(cnt.reshape(32, 4), rx).reshape(128)
+    x = np.arange(pad, 128 - pad)
+    np.testing.assert_array_equal(win[x], np.array([cnt[i - rx:i + rx + 1].sum() for i in x]))
+
+
 def test_focal_mean_division_by_count_is_correctly_rounded():
     """div_count9 (surface_ops.cuh) replaces the float64 division s / n (n = 1..9 valid cells) by
     q = s * (1/n), e = fma(-q, n, s), q + e * (1/n): with exact FMAs (emulated here with rationals)

@@ -61,6 +61,7 @@ def _declare(lib):
         "xrs_zonal_hash_init": [P, P, P, P, P, P, I, P, P],
         "xrs_zonal_hash_accumulate": [P, I, P, I, I64, I64, D, I, D, P, P, P, P, P, P, I, P, P],
         "xrs_zonal_hash_run": [P, I, P, I, I64, I64, I, D, I, D, P, P, P, P, P, P, I, P, I, P, P],
+        "xrs_zonal_hash_second_pass": [P, I, P, I, I64, I64, I, D, P, P, P, P, P, P, P, I, P, I, P, P],
         "xrs_zonal_pair_count": [P, P, I64, I64, I, D, P, P, I, P, P],
         "xrs_host_stencil": [I, P, P, I64, I64, P, P, I, I],
         "xrs_host_surface_typed": [I, P, I, P, I64, I64, P, I],

@@ -411,6 +411,374 @@ static int launch_box_stream(const CUtensorMap &tmap, const float *in, int64_t i
     return XRS_OK;
 }
 
+// ============================================================================================
+// Second generation (round 2, second session): the same running box, reorganised around what the
+// ncu / SASS reading of the kernel above showed (36 instructions per cell, a third of them register
+// moves and the 5-step float64 warp scan; issue slots 35 % busy behind long shuffle / add chains; for
+// k = 25 a ring that holds the whole window leaves 4 rows of prefetch):
+//   * LANE SUMS instead of a prefix scan.  A lane forms the inclusive prefix `pre` and suffix `suf` of
+//     its own 4 column sums and its total; the window of column 4l + j then is
+//         suf[.] of the lane its left end falls in + pre[.] of the lane its right end falls in
+//         + the totals of the whole lanes in between,
+//     every operand at a compile-time lane distance: 4 (k = 5) ... 11 (k = 25) float64 shuffles per
+//     lane-row instead of 13, no 5-step dependent scan, no prefix differences.  A NaN that lives in
+//     one lane's sums reaches exactly the windows that contain that lane's columns, so the columns
+//     beyond the raster's left / right edge (NaN from the TMA unit) need no masking: edge tiles run
+//     the fast path and their border windows come out NaN like the reference's.
+//   * TWO STREAMS per stage: the 4 rows that enter the window and the 4 rows that leave it (re-read
+//     through L2, they were fetched kh rows earlier by the same CTA) arrive as ONE stage with one
+//     full / one empty mbarrier -- the ring no longer holds the window, so k = 25 gets the same 3
+//     stages of prefetch as k = 5, and a consumer warp waits and arrives once per 4 rows.
+//   * one 3-input NaN-propagating |max| chain (FMNMX3.NAN) finds NaN / inf / huge cells.
+//   * segments are chosen so that no CTA runs one task more than the others (pick_seg_rows).
+constexpr int kB2Rows = 4;              // rows per stage half (entering / leaving)
+constexpr int kBoxNotTaken = -12345;
+
+// XRS_BOX_ALGO=1 selects the first-generation (prefix-scan, window-in-ring) kernel, for A/B measurements
+static int box_algo() {
+    const char *e = getenv("XRS_BOX_ALGO");
+    return (e && atoi(e) == 1) ? 1 : 2;
+}
+
+template <int RX> struct B2Shape {
+    static constexpr int kPad = (RX + 3) / 4 * 4;               // columns a warp cannot emit on each side
+    static constexpr int kOutW = kStripW - 2 * kPad;            // columns a warp emits
+    static constexpr int kTileOutW = kBsWarps * kOutW;
+    static constexpr int kTileInW = kTileOutW + 2 * kPad;
+    static constexpr int kNBox = (kTileInW + 255) / 256;
+    static constexpr int kBoxW = ((kTileInW + kNBox - 1) / kNBox + 31) / 32 * 32;   // cells: 128-byte multiples
+    static constexpr int kBoxCells = kB2Rows * kBoxW;           // one TMA box: 4 rows x kBoxW cells
+    static constexpr int kHalfCells = kNBox * kBoxCells;        // the entering (or leaving) rows of a stage
+    static constexpr uint32_t kHalfBytes = kHalfCells * 4;
+    static_assert(kBoxW <= 256 && kBoxW % 32 == 0 && kNBox * kBoxW >= kTileInW, "TMA box geometry");
+};
+
+struct B2Geom {
+    int64_t H, W;
+    int kh, ry;
+    int n_tiles, n_segs, seg_rows;
+    int stages;
+    double w;
+};
+
+// max(|a|, |b|, |c|), NaN if any operand is NaN (FMNMX3.NAN with |.| operand modifiers)
+__device__ __forceinline__ float bs_amax3(float a, float b, float c) {
+    float r;
+    asm("{\n.reg .f32 x, y, z;\nabs.f32 x, %1;\nabs.f32 y, %2;\nabs.f32 z, %3;\nmax.NaN.f32 %0, x, y, z;\n}"
+        : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float bs_amax4(const float (&v)[4]) {
+    return bs_amax3(bs_amax3(v[0], v[1], v[2]), v[3], v[3]);
+}
+
+// the value lane (l + D) holds; lanes past the warp's ends get their own (they sit in the pad)
+template <int D, typename T> __device__ __forceinline__ T bs_from(T x) {
+    if constexpr (D == 0) return x;
+    else if constexpr (D > 0) return __shfl_down_sync(0xffffffffu, x, D);
+    else return __shfl_up_sync(0xffffffffu, x, -D);
+}
+
+// window sum of column 4 l + J (radius RX) from the lane-local prefix / suffix sums, the lane total,
+// `core` = the totals of lanes l-q+1 .. l+q-1, `tl` / `tr` = the totals of lanes l-q / l+q  (q = RX / 4)
+template <int RX, int J, typename T>
+__device__ __forceinline__ T bs_cell(const T (&pre)[4], const T (&suf)[4], T tot, T core, T tl, T tr) {
+    constexpr int q = RX / 4, m = RX % 4;
+    constexpr int a = J - m, b = J + m;          // window = [4 (l - q) + a, 4 (l + q) + b]
+    if constexpr (q == 0 && a >= 0 && b <= 3) {  // inside the lane (RX = 1 only)
+        static_assert(a == 0 || b == 3, "in-lane window");
+        if constexpr (a == 0) return pre[b]; else return suf[a];
+    } else {
+        constexpr int dl = -q - (a < 0 ? 1 : 0), ia = (a + 4) & 3;
+        constexpr int dh = q + (b >= 4 ? 1 : 0), ib = b & 3;
+        const T ends = bs_from<dl>(suf[ia]) + bs_from<dh>(pre[ib]);
+        if constexpr (q == 0) {
+            if constexpr (a < 0 && b >= 4) return ends + tot; else return ends;
+        } else {
+            T full = core;
+            if constexpr (a < 0) full = full + tl;
+            if constexpr (b >= 4) full = full + tr;
+            return ends + full;
+        }
+    }
+}
+
+// win[i][j] = sum of v[i] over columns 4 l + j - RX .. 4 l + j + RX, for R independent rows (their
+// shuffle / add chains interleave)
+template <int RX, int R, typename T>
+__device__ __forceinline__ void bs_lanesum(const T (&v)[R][4], T (&win)[R][4]) {
+    static_assert(RX >= 1 && RX <= 12, "window radius");
+    constexpr int q = RX / 4, m = RX % 4;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        T pre[4], suf[4];
+        pre[0] = v[i][0];
+        pre[1] = pre[0] + v[i][1];
+        pre[2] = pre[1] + v[i][2];
+        pre[3] = pre[2] + v[i][3];
+        suf[3] = v[i][3];
+        suf[2] = v[i][2] + suf[3];
+        suf[1] = v[i][1] + suf[2];
+        suf[0] = pre[3];
+        const T tot = pre[3];
+        T core = tot, tl = T(0), tr = T(0);
+        if constexpr (q == 2) core = (bs_from<-1>(tot) + tot) + bs_from<1>(tot);
+        if constexpr (q == 3) {
+            const T pair = tot + bs_from<1>(tot);                       // lanes l, l + 1
+            core = (bs_from<-2>(pair) + pair) + bs_from<2>(tot);        // lanes l - 2 .. l + 2
+        }
+        if constexpr (q >= 1 && m > 0) {
+            tl = bs_from<-q>(tot);
+            tr = bs_from<q>(tot);
+        }
+        win[i][0] = bs_cell<RX, 0, T>(pre, suf, tot, core, tl, tr);
+        win[i][1] = bs_cell<RX, 1, T>(pre, suf, tot, core, tl, tr);
+        win[i][2] = bs_cell<RX, 2, T>(pre, suf, tot, core, tl, tr);
+        win[i][3] = bs_cell<RX, 3, T>(pre, suf, tot, core, tl, tr);
+    }
+}
+
+__device__ __forceinline__ uint32_t bs_bits(int n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
+
+template <int RX>
+__global__ void __launch_bounds__((kBsWarps + 1) * 32, 2)
+box_stream2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ in, int64_t in_pitch_elems,
+                   float *__restrict__ out, int64_t out_pitch_elems, const B2Geom g) {
+    using S = B2Shape<RX>;
+    constexpr int kw = 2 * RX + 1;
+    constexpr int kStageCells = 2 * S::kHalfCells;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float *ring = reinterpret_cast<float *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)g.stages * kStageCells * sizeof(float));
+    uint64_t *empty = full + g.stages;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kBsWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int64_t n_tasks = (int64_t)g.n_tiles * g.n_segs;
+    const int kh = g.kh, ry = g.ry;
+
+    if (warp == kBsWarps) {
+        // ---- producer: per task the batches of 4 entering rows e0 .. e0 + 3 (row e = raster row
+        // y0 - ry + e) and, once rows leave the window, the 4 rows e0 - (kh - 1) .. that leave with them
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t lap = 0;
+            for (int64_t task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+                const int seg = (int)(task / g.n_tiles), tile = (int)(task % g.n_tiles);
+                const int64_t y0 = (int64_t)seg * g.seg_rows, y1 = min(y0 + (int64_t)g.seg_rows, g.H);
+                const int bx = tile * S::kTileOutW - S::kPad;
+                const int ytop = (int)y0 - ry;
+                const int n_in = (int)(y1 - y0) + kh - 1;
+                for (int e0 = 0; e0 < n_in; e0 += kB2Rows) {
+                    mbar_wait(&empty[stage], lap ^ 1u);  // a fresh barrier passes the first lap
+                    const bool leaving = e0 + kB2Rows - 1 >= kh - 1;
+                    mbar_arrive_expect_tx(&full[stage], leaving ? 2u * S::kHalfBytes : S::kHalfBytes);
+                    float *dst = ring + (size_t)stage * kStageCells;
+#pragma unroll
+                    for (int b = 0; b < S::kNBox; ++b)
+                        tma_load_2d(dst + b * S::kBoxCells, &tmap, &full[stage], bx + b * S::kBoxW, ytop + e0);
+                    if (leaving) {
+#pragma unroll
+                        for (int b = 0; b < S::kNBox; ++b)
+                            tma_load_2d(dst + S::kHalfCells + b * S::kBoxCells, &tmap, &full[stage], bx + b * S::kBoxW,
+                                        ytop + e0 - (kh - 1));
+                    }
+                    if (++stage == g.stages) { stage = 0; lap ^= 1u; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- consumers
+    const int col = warp * S::kOutW + 4 * lane;                         // first of the lane's columns in the tile row
+    const int off = (col / S::kBoxW) * S::kBoxCells + (col % S::kBoxW);  // + i * kBoxW for row i of the half
+    const bool emits = (4 * lane >= S::kPad) && (4 * lane < kStripW - S::kPad);
+    const uint32_t win_mask = bs_bits(kh - 1);   // the rows in the window before a row is added
+    int stage = 0;
+    uint32_t lap = 0;
+    for (int64_t task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+        const int seg = (int)(task / g.n_tiles), tile = (int)(task % g.n_tiles);
+        const int64_t y0 = (int64_t)seg * g.seg_rows, y1 = min(y0 + (int64_t)g.seg_rows, g.H);
+        const int64_t x = (int64_t)tile * S::kTileOutW - S::kPad + col;  // raster column of the lane's first cell
+        const bool in_raster = x >= 0 && x < g.W;                          // W % 4 == 0: all four cells in or out
+        const bool store_ok = emits && in_raster;
+        float *optr = out + y0 * out_pitch_elems + x;
+
+        double V[4] = {0.0, 0.0, 0.0, 0.0};
+        unsigned C[4] = {0u, 0u, 0u, 0u};   // lo 16 bits: NaN cells in the column window, hi 16: infinite / huge
+        uint32_t dirty = 0;                  // bit i: the row added i rows ago held a NaN / inf / huge cell (this warp)
+        const int n_in = (int)(y1 - y0) + kh - 1;
+        for (int e0 = 0; e0 < n_in; e0 += kB2Rows) {
+            mbar_wait(&full[stage], lap);
+            const float *se = ring + (size_t)stage * kStageCells + off;   // entering rows
+            const float *sl = se + S::kHalfCells;                          // leaving rows
+            bool done = false;
+            if (e0 >= kh - 1 && e0 + kB2Rows <= n_in && (dirty & win_mask) == 0u) {
+                // ---- fast path: window complete, 4 rows enter, 4 rows are emitted, 4 rows leave; neither
+                // the window nor the entering rows hold a NaN / inf / huge cell inside the raster
+                float nv[kB2Rows][4];
+#pragma unroll
+                for (int i = 0; i < kB2Rows; ++i) {
+                    const float4 q = *reinterpret_cast<const float4 *>(se + i * S::kBoxW);
+                    nv[i][0] = q.x; nv[i][1] = q.y; nv[i][2] = q.z; nv[i][3] = q.w;
+                }
+                const float amax = bs_amax3(bs_amax3(bs_amax4(nv[0]), nv[1][0], nv[1][1]),
+                                            bs_amax3(bs_amax4(nv[2]), nv[1][2], nv[1][3]), bs_amax4(nv[3]));
+                if (!__any_sync(0xffffffffu, in_raster && !(amax < kBsHuge))) {
+                    float ov[kB2Rows][4];
+#pragma unroll
+                    for (int i = 0; i < kB2Rows; ++i) {
+                        const float4 q = *reinterpret_cast<const float4 *>(sl + i * S::kBoxW);
+                        ov[i][0] = q.x; ov[i][1] = q.y; ov[i][2] = q.z; ov[i][3] = q.w;
+                    }
+                    // column sums of output row i: V_i = V_{i-1} - old_{i-1} + new_i
+                    double P[kB2Rows][4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        double acc = V[j];
+#pragma unroll
+                        for (int i = 0; i < kB2Rows; ++i) {
+                            const double d = (i == 0) ? (double)nv[0][j] : ((double)nv[i][j] - (double)ov[i > 0 ? i - 1 : 0][j]);
+                            acc += d;
+                            P[i][j] = acc;
+                        }
+                        V[j] = acc - (double)ov[kB2Rows - 1][j];
+                    }
+                    double win[kB2Rows][4];
+                    bs_lanesum<RX, kB2Rows, double>(P, win);
+#pragma unroll
+                    for (int i = 0; i < kB2Rows; ++i) {
+                        if (store_ok)
+                            __stcs(reinterpret_cast<float4 *>(optr),
+                                   make_float4((float)fma(g.w, win[i][0], 0.0), (float)fma(g.w, win[i][1], 0.0),
+                                               (float)fma(g.w, win[i][2], 0.0), (float)fma(g.w, win[i][3], 0.0)));
+                        optr += out_pitch_elems;
+                    }
+                    dirty <<= kB2Rows;
+                    done = true;
+                }
+            }
+            if (!done) {
+                // ---- row by row: lead-in rows (nothing to emit yet), the last rows of a task, and windows
+                // or entering rows with NaN / inf / huge cells (kept out of V, counted in C)
+                for (int i = 0; i < kB2Rows; ++i) {
+                    const int e = e0 + i;
+                    if (e >= n_in) break;
+                    const float4 q = *reinterpret_cast<const float4 *>(se + i * S::kBoxW);
+                    const float v[4] = {q.x, q.y, q.z, q.w};
+                    const bool row_dirty = __any_sync(0xffffffffu, in_raster && !(bs_amax4(v) < kBsHuge));
+                    dirty = (dirty << 1) | (row_dirty ? 1u : 0u);
+                    if (!row_dirty) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) V[j] += (double)v[j];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const bool isnan_ = v[j] != v[j];
+                            const bool big = !isnan_ && !(fabsf(v[j]) < kBsHuge);
+                            V[j] += (isnan_ || big) ? 0.0 : (double)v[j];
+                            C[j] += isnan_ ? 1u : (big ? 0x10000u : 0u);
+                        }
+                    }
+                    if (e < kh - 1) continue;   // window not complete yet
+
+                    // emit output row y = y0 + e - (kh - 1)
+                    const bool win_dirty = (dirty & bs_bits(kh)) != 0u;
+                    double P1[1][4] = {{V[0], V[1], V[2], V[3]}}, w1[1][4];
+                    bs_lanesum<RX, 1, double>(P1, w1);
+                    float res[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) res[j] = (float)fma(g.w, w1[0][j], 0.0);   // + 0.0: an all-zero window is +0 like the reference's
+                    if (win_dirty) {   // warp-uniform
+                        unsigned C1[1][4] = {{C[0], C[1], C[2], C[3]}}, wc[1][4];
+                        bs_lanesum<RX, 1, unsigned>(C1, wc);
+                        const int64_t y = y0 + e - (kh - 1);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (wc[0][j] & 0xffffu) res[j] = nan_of<float>();
+                            else if (wc[0][j] >> 16) {
+                                if (store_ok) res[j] = bs_direct(in, in_pitch_elems, g.H, g.W, y, x + j, kh, kw, g.w);
+                            }
+                        }
+                    }
+                    if (store_ok) __stcs(reinterpret_cast<float4 *>(optr), make_float4(res[0], res[1], res[2], res[3]));
+                    optr += out_pitch_elems;
+
+                    // retire input row e - (kh - 1), the oldest row of the window
+                    const float4 qo = *reinterpret_cast<const float4 *>(sl + i * S::kBoxW);
+                    const float vo[4] = {qo.x, qo.y, qo.z, qo.w};
+                    const bool old_dirty = (dirty >> (kh - 1)) & 1u;
+                    if (!old_dirty) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) V[j] -= (double)vo[j];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const bool isnan_ = vo[j] != vo[j];
+                            const bool big = !isnan_ && !(fabsf(vo[j]) < kBsHuge);
+                            V[j] -= (isnan_ || big) ? 0.0 : (double)vo[j];
+                            C[j] -= isnan_ ? 1u : (big ? 0x10000u : 0u);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == g.stages) { stage = 0; lap ^= 1u; }
+        }
+    }
+}
+
+template <int RX>
+static int launch_box_stream2(const float *in, int64_t in_pitch, float *out, int64_t out_pitch, int64_t H, int64_t W,
+                              int kh, double w, cudaStream_t s) {
+    using S = B2Shape<RX>;
+    CUtensorMap tmap;
+    if (!make_tensor_map_2d(&tmap, in, in_pitch, H, W, 4, S::kBoxW, kB2Rows)) return kBoxNotTaken;
+    B2Geom g;
+    g.H = H; g.W = W; g.kh = kh; g.ry = kh / 2; g.w = w;
+    g.n_tiles = (int)((W + S::kTileOutW - 1) / S::kTileOutW);
+    int stages = 3, max_ctas = 2, want = 4;
+    if (const char *e = getenv("XRS_BOX_STAGES")) stages = atoi(e);
+    if (const char *e = getenv("XRS_BOX_CTAS")) max_ctas = atoi(e);
+    if (const char *e = getenv("XRS_BOX_WAVES")) want = atoi(e);
+    if (max_ctas < 1) max_ctas = 1;
+    if (want < 1) want = 1;
+    const size_t stage_bytes = (size_t)2 * S::kHalfBytes;
+    const size_t cap = (size_t)(224 * 1024) / max_ctas;
+    if (stages < 2) stages = 2;
+    while (stages > 2 && (size_t)stages * stage_bytes + (size_t)2 * stages * sizeof(uint64_t) > cap) --stages;
+    g.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + (size_t)2 * stages * sizeof(uint64_t);
+    auto kern = box_stream2_kernel<RX>;
+    XRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (kBsWarps + 1) * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > max_ctas) per_sm = max_ctas;
+    const int64_t resident = (int64_t)sm_count() * per_sm;
+    // segments: tall enough that the kh - 1 lead-in rows stay a small overhead, (rows + kh - 1) a
+    // multiple of 4 so that only the raster's last segment ends in a partial batch
+    const int64_t seg_rows = pick_seg_rows(H, g.n_tiles, resident, 12 * (int64_t)kh, kh - 1, kB2Rows, want);
+    g.seg_rows = (int)seg_rows;
+    g.n_segs = (int)((H + seg_rows - 1) / seg_rows);
+    const int64_t n_tasks = (int64_t)g.n_tiles * g.n_segs;
+    const int64_t grid = resident < n_tasks ? resident : n_tasks;
+    kern<<<(unsigned)grid, (kBsWarps + 1) * 32, smem, s>>>(tmap, in, in_pitch / 4, out, out_pitch / 4, g);
+    last_launch_info() = {3, (int)grid, (kBsWarps + 1) * 32, (int)smem};
+    XRS_CUDA(cudaGetLastError());
+    return XRS_OK;
+}
+
 // true when the streaming box kernel took the job (*rc = its status)
 bool try_box_stream(const float *in, int64_t in_pitch, float *out, int64_t out_pitch, int64_t H, int64_t W,
                     const double *kernel, int kh, int kw, cudaStream_t s, int *rc) {
@@ -421,14 +789,18 @@ bool try_box_stream(const float *in, int64_t in_pitch, float *out, int64_t out_p
         if (memcmp(&kernel[i], &w, sizeof(double)) != 0) return false;
     if (W % 4 != 0 || out_pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(out) & 15)) return false;
     if (H >= (1LL << 31) - 64 || W >= (1LL << 31) - 4096) return false;
+    if (box_algo() == 2) {
+        switch (kw / 2) {
+#define XRS_BS(R) case R: { const int r2 = launch_box_stream2<R>(in, in_pitch, out, out_pitch, H, W, kh, w, s); \
+                            if (r2 != kBoxNotTaken) { *rc = r2; return true; } } break;
+            XRS_BS(1) XRS_BS(2) XRS_BS(3) XRS_BS(4) XRS_BS(5) XRS_BS(6) XRS_BS(7) XRS_BS(8) XRS_BS(9) XRS_BS(10) XRS_BS(11) XRS_BS(12)
+#undef XRS_BS
+        }
+    }
     CUtensorMap tmap;
     if (!make_tensor_map_2d(&tmap, in, in_pitch, H, W, 4, kBsBoxW, 1)) return false;
-    int kr = 4;
-    if (const char *e = getenv("XRS_BOX_ROWS")) kr = atoi(e);
     switch (kw / 2) {
-#define XRS_BS(R) case R: *rc = kr == 8 ? launch_box_stream<R, 8>(tmap, in, in_pitch, out, out_pitch, H, W, kh, w, s) \
-                             : kr == 6 ? launch_box_stream<R, 6>(tmap, in, in_pitch, out, out_pitch, H, W, kh, w, s) \
-                                       : launch_box_stream<R, 4>(tmap, in, in_pitch, out, out_pitch, H, W, kh, w, s); return true;
+#define XRS_BS(R) case R: *rc = launch_box_stream<R, 4>(tmap, in, in_pitch, out, out_pitch, H, W, kh, w, s); return true;
         XRS_BS(1) XRS_BS(2) XRS_BS(3) XRS_BS(4) XRS_BS(5) XRS_BS(6) XRS_BS(7) XRS_BS(8) XRS_BS(9) XRS_BS(10) XRS_BS(11) XRS_BS(12)
 #undef XRS_BS
     }

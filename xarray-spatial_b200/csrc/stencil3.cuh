@@ -451,20 +451,51 @@ stencil3_cpasync_kernel(const typename Op::in_t *__restrict__ in, int64_t in_pit
 }
 
 // ----------------------------------------------------------------------------- host launcher
-// Row segments: ~8 tasks per resident CTA, but segments of >= 32 rows so the 2 halo rows re-read per
-// segment stay a small overhead; a multiple of ROWS (minus the 2 lead-in rows) so the last chunk of a
-// segment wastes < ROWS rows.
+// Row segments.  Tasks (tiles x segments) are dealt round-robin to `resident` persistent CTAs, so a kernel
+// lasts ceil(tasks / resident) task-times ("waves"): one task too many costs a whole extra wave (1188 tasks on
+// 1184 task slots ran 9 waves instead of 8.03: the round-2 fused suite lost 11 % to that).  Pick the
+// segment height that minimises waves x (rows + lead-in rows a task streams), among heights of at least
+// `min_rows` with (rows + lead) a multiple of `quantum` (so the last chunk of a segment is full); among
+// heights within 1 % of the best prefer ~`want` waves (short tasks even out the partly filled last tile).
+inline int64_t pick_seg_rows(int64_t H, int64_t n_tiles, int64_t resident, int64_t min_rows, int64_t lead,
+                             int64_t quantum, int64_t want) {
+    if (H <= 0) return 1;
+    if (resident < 1) resident = 1;
+    if (min_rows > H) min_rows = H;
+    if (min_rows < 1) min_rows = 1;
+    int64_t cmax = H / min_rows;
+    const int64_t ccap = (resident * 4 * want) / (n_tiles > 0 ? n_tiles : 1) + 2;
+    if (cmax > ccap) cmax = ccap;
+    if (cmax < 1) cmax = 1;
+    double best = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+        int64_t pick = 0, pick_d = 0;
+        for (int64_t c = 1; c <= cmax; ++c) {
+            int64_t rows = (H + c - 1) / c;
+            if (rows < min_rows) rows = min_rows;
+            rows = ((rows + lead + quantum - 1) / quantum) * quantum - lead;
+            if (rows < 1) rows = 1;
+            const int64_t segs = (H + rows - 1) / rows;
+            const int64_t waves = (segs * n_tiles + resident - 1) / resident;
+            const double cost = (double)waves * (double)(rows + lead);
+            if (pass == 0) {
+                if (best == 0.0 || cost < best) best = cost;
+            } else if (cost <= best * 1.01) {
+                const int64_t d = waves > want ? waves - want : want - waves;
+                if (pick == 0 || d < pick_d) { pick = rows; pick_d = d; }
+            }
+        }
+        if (pass == 1) return pick > 0 ? pick : H;
+    }
+    return H;
+}
+
 inline TileGeom make_tile_geom(int64_t H, int64_t W, int tile_w, int rows, int64_t resident_ctas) {
     TileGeom g;
     g.H = H;
     g.W = W;
     g.n_tiles = (int)((W + tile_w - 1) / tile_w);
-    int64_t want_segs = (resident_ctas * 8 + g.n_tiles - 1) / g.n_tiles;
-    int64_t seg_rows = (H + want_segs - 1) / (want_segs > 0 ? want_segs : 1);
-    if (seg_rows < 32) seg_rows = 32;
-    if (seg_rows > H) seg_rows = H;
-    seg_rows = ((seg_rows + 2 + rows - 1) / rows) * rows - 2;
-    if (seg_rows < 1) seg_rows = 1;
+    const int64_t seg_rows = pick_seg_rows(H, g.n_tiles, resident_ctas, 32, 2, rows, 8);
     g.seg_rows = (int)seg_rows;
     g.n_segs = (int)((H + seg_rows - 1) / seg_rows);
     return g;

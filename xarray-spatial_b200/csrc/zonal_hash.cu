@@ -30,6 +30,8 @@ struct ZhArgs {
     int64_t W;      // row length of the raster (n = H * W); walking DOWN columns keeps runs long
     double pivot;
     const double *pivot_ptr;   // when not NULL the pivot is read from device memory (xrs_zonal_hash_run)
+    const double *zone_pivots; // when not NULL: one pivot per slot of the (already populated) global table --
+                               // the second pass of float64 rasters, sums about the zones' own means
     int has_nodata;
     double nodata;
     long long *keys;
@@ -112,6 +114,18 @@ __device__ __forceinline__ int zh_slot(long long *keys, int cap, long long key, 
     return -1;
 }
 
+// read-only lookup in a populated table; -1 when the key is absent
+__device__ __forceinline__ int zh_find(const long long *keys, int cap, long long key) {
+    unsigned s = zh_hash(key) & (unsigned)(cap - 1);
+    for (int p = 0; p < cap; ++p) {
+        const long long k = keys[s];
+        if (k == key) return (int)s;
+        if (k == kZhEmpty) return -1;
+        s = (s + 1) & (unsigned)(cap - 1);
+    }
+    return -1;
+}
+
 template <typename ZT> __device__ __forceinline__ bool zh_key(ZT z, long long &key) {
     if constexpr (sizeof(ZT) == 4 && ZT(0.5) == ZT(0)) {  // int32
         key = (long long)z;
@@ -148,9 +162,9 @@ template <typename VT> __device__ __forceinline__ bool zh_valid(VT v, const ZhAr
     else return (fabs(v) <= 1.7976931348623157e308) && !(a.has_nodata && v == a.nodata);
 }
 
-template <typename VT> __device__ __forceinline__ void zh_add(ZhRun &r, VT v, const ZhArgs &a) {
+template <typename VT> __device__ __forceinline__ void zh_add(ZhRun &r, VT v, const ZhArgs &a, double pivot) {
     if (zh_valid<VT>(v, a)) {
-        const double d = (double)v - a.pivot;
+        const double d = (double)v - pivot;
         r.s1 += d;
         r.s2 = fma(d, d, r.s2);
         if constexpr (sizeof(VT) == 4) {
@@ -165,13 +179,13 @@ template <typename VT> __device__ __forceinline__ void zh_add(ZhRun &r, VT v, co
 }
 
 // four cells of one zone at once, branch-free, with short dependency chains (tree sums)
-template <typename VT> __device__ __forceinline__ void zh_add4(ZhRun &r, const VT (&v)[4], const ZhArgs &a) {
+template <typename VT> __device__ __forceinline__ void zh_add4(ZhRun &r, const VT (&v)[4], const ZhArgs &a, double pivot) {
     bool ok[4];
     double d[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         ok[k] = zh_valid<VT>(v[k], a);
-        d[k] = ok[k] ? (double)v[k] - a.pivot : 0.0;
+        d[k] = ok[k] ? (double)v[k] - pivot : 0.0;
     }
     r.s1 += (d[0] + d[1]) + (d[2] + d[3]);
     r.s2 += fma(d[0], d[0], d[1] * d[1]) + fma(d[2], d[2], d[3] * d[3]);
@@ -238,6 +252,7 @@ __global__ void __launch_bounds__(kZhThreads, 3) zonal_hash_kernel(const __grid_
     ZT cur_z = ZT(0);
     bool have = false, cur_ok = false;
     long long cur_key = 0;
+    double cur_p = a.pivot;   // the shift of the lane's current run: global, or its zone's (second pass)
 
     // merge (key, cnt, s1, s2, mn, mx) into the CTA table, spilling to the global table when the
     // CTA sees more distinct zones than its table holds
@@ -360,11 +375,15 @@ __global__ void __launch_bounds__(kZhThreads, 3) zonal_hash_kernel(const __grid_
                             cur_z = zk;
                             have = (zk == zk);
                             cur_ok = zh_key<ZT>(zk, cur_key);
+                            if (a.zone_pivots != nullptr && cur_ok) {
+                                const int ps = zh_find(a.keys, a.cap, cur_key);
+                                cur_p = ps >= 0 ? a.zone_pivots[ps] : a.pivot;
+                            }
                         }
-                        if (live && cur_ok) zh_add<VT>(run, v[u].v[k], a);
+                        if (live && cur_ok) zh_add<VT>(run, v[u].v[k], a, cur_p);
                     }
                 } else if (fast && cur_ok) {
-                    zh_add4<VT>(run, v[u].v, a);
+                    zh_add4<VT>(run, v[u].v, a, cur_p);
                 }
             }
         }
@@ -448,19 +467,44 @@ __global__ void __launch_bounds__(kZhThreads) zonal_pair_kernel(const __grid_con
         const int64_t x = strip * 128 + 4 * lane;
         const int64_t y0 = seg * kZhSegRows, y1 = min(y0 + (int64_t)kZhSegRows, H);
         const int nv = (int)max((int64_t)0, min((int64_t)4, a.W - x));
-        for (int64_t y = y0; y < y1; ++y) {
-            const int64_t i0 = y * a.W + x;
-            const ZhQuad<float> v = zh_load<float>(a.values, i0, i0 + nv, al);
-            const ZhQuad<int> z = zh_load<int>(a.zones, i0, i0 + nv, al);
+        // kZhUnroll rows of 128-bit loads in flight per lane (the row-at-a-time version of round 1 sat at
+        // 0.23-0.26 of the HBM roofline, waiting on one load pair per iteration), and a vote-only fast path
+        // for rows in which no lane meets a new (zone, value) pair
+        for (int64_t y = y0; y < y1; y += kZhUnroll) {
+            ZhQuad<float> v[kZhUnroll];
+            ZhQuad<int> z[kZhUnroll];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float f = v.v[k] + 0.0f;  // -0.0 -> +0.0
-                const bool ok = k < nv && (fabsf(f) <= 3.402823466e38f) && !(a.has_nodata && f == a.nodata);
-                const long long key = ((long long)z.v[k] << 32) | (long long)__float_as_uint(f);
-                const bool change = ok && key != cur_key;
-                if (__any_sync(0xffffffffu, change)) flush_all(change);
-                if (change) cur_key = key;
-                if (ok) run += 1u;
+            for (int u = 0; u < kZhUnroll; ++u) {
+                const int64_t i0 = (y + u) * a.W + x;
+                const int nvu = (y + u < y1) ? nv : 0;
+                v[u] = zh_load<float>(a.values, i0, i0 + nvu, al);
+                z[u] = zh_load<int>(a.zones, i0, i0 + nvu, al);
+            }
+#pragma unroll
+            for (int u = 0; u < kZhUnroll; ++u) {
+                const int nvu = (y + u < y1) ? nv : 0;
+                bool ok[4], change = false;
+                long long key[4];
+                unsigned n_ok = 0u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float f = v[u].v[k] + 0.0f;  // -0.0 -> +0.0
+                    ok[k] = k < nvu && (fabsf(f) <= 3.402823466e38f) && !(a.has_nodata && f == a.nodata);
+                    key[k] = ((long long)z[u].v[k] << 32) | (long long)__float_as_uint(f);
+                    change = change || (ok[k] && key[k] != cur_key);
+                    n_ok += ok[k] ? 1u : 0u;
+                }
+                if (!__any_sync(0xffffffffu, change)) {
+                    run += n_ok;         // every valid cell of every lane continues its lane's run
+                    continue;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool ch = ok[k] && key[k] != cur_key;
+                    if (__any_sync(0xffffffffu, ch)) flush_all(ch);
+                    if (ch) cur_key = key[k];
+                    if (ok[k]) run += 1u;
+                }
             }
         }
     }
@@ -483,6 +527,16 @@ __global__ void zonal_hash_init_kernel(long long *keys, unsigned long long *coun
         s1[i] = 0.0; s2[i] = 0.0; vmin[i] = INFINITY; vmax[i] = -INFINITY;
     }
     if (i == 0) *overflow = 0;
+}
+
+// accumulators back to empty, keys kept (second pass over a populated table)
+__global__ void zonal_hash_reset_kernel(unsigned long long *count, double *s1, double *s2, double *vmin, double *vmax,
+                                        int cap) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) {
+        count[i] = 0ull;
+        s1[i] = 0.0; s2[i] = 0.0; vmin[i] = INFINITY; vmax[i] = -INFINITY;
+    }
 }
 
 // ---- one-call front end: pivot sampling, table compaction and header, all on the device ----------
@@ -585,6 +639,7 @@ int xrs_zonal_hash_accumulate(const void *values, int values_dtype, const void *
     XRS_REQUIRE(row_len >= 1 && n % row_len == 0, "n must be a multiple of row_len");
     ZhArgs a;
     a.values = values; a.zones = zones; a.n = n; a.W = row_len; a.pivot = pivot; a.pivot_ptr = nullptr;
+    a.zone_pivots = nullptr;
     a.has_nodata = has_nodata; a.nodata = nodata;
     a.keys = (long long *)keys; a.count = (unsigned long long *)count; a.s1 = s1; a.s2 = s2; a.vmin = vmin;
     a.vmax = vmax; a.cap = cap; a.overflow = overflow;
@@ -624,9 +679,51 @@ int xrs_zonal_hash_run(const void *values, int values_dtype, const void *zones, 
     XRS_CUDA(cudaGetLastError());
     ZhArgs a;
     a.values = values; a.zones = zones; a.n = n; a.W = row_len; a.pivot = 0.0; a.pivot_ptr = pivot_dev;
+    a.zone_pivots = nullptr;
     a.has_nodata = has_nodata; a.nodata = nodata;
     a.keys = (long long *)keys; a.count = (unsigned long long *)count; a.s1 = s1; a.s2 = s2; a.vmin = vmin;
     a.vmax = vmax; a.cap = cap; a.overflow = flags;
+    int rc;
+#define XRS_ZH(VT)                                                               \
+    switch (zones_dtype) {                                                       \
+        case XRS_I32: rc = launch_zh<VT, int>(a, st); break;                     \
+        case XRS_I64: rc = launch_zh<VT, long long>(a, st); break;               \
+        case XRS_F32: rc = launch_zh<VT, float>(a, st); break;                   \
+        default: rc = launch_zh<VT, double>(a, st); break;                       \
+    }
+    if (values_dtype == XRS_F32) { XRS_ZH(float) } else { XRS_ZH(double) }
+#undef XRS_ZH
+    if (rc != XRS_OK) return rc;
+    zonal_compact_kernel<<<(cap + 255) / 256, 256, 0, st>>>((const long long *)keys, (const unsigned long long *)count,
+                                                           s1, s2, vmin, vmax, cap, packed, max_out, flags);
+    zonal_header_kernel<<<1, 1, 0, st>>>(packed, flags, pivot_dev);
+    XRS_CUDA(cudaGetLastError());
+    return XRS_OK;
+}
+
+int xrs_zonal_hash_second_pass(const void *values, int values_dtype, const void *zones, int zones_dtype, int64_t n,
+                               int64_t row_len, int has_nodata, double nodata, const int64_t *keys,
+                               const double *zone_pivots, int64_t *count, double *s1, double *s2, double *vmin,
+                               double *vmax, int cap, double *packed, int max_out, int *flags, xrs_stream_t s) {
+    XRS_REQUIRE(values && zones && keys && zone_pivots && count && s1 && s2 && vmin && vmax && packed && flags,
+                "NULL pointer");
+    XRS_REQUIRE(values_dtype == XRS_F32 || values_dtype == XRS_F64, "values must be float32 or float64");
+    XRS_REQUIRE(zones_dtype >= XRS_F32 && zones_dtype <= XRS_I64, "unknown zones dtype");
+    XRS_REQUIRE(cap >= 1024 && (cap & (cap - 1)) == 0, "cap must be a power of two >= 1024");
+    XRS_REQUIRE(max_out >= 1, "max_out must be positive");
+    XRS_REQUIRE(n >= 1 && row_len >= 1 && n % row_len == 0, "n must be a positive multiple of row_len");
+    cudaStream_t st = (cudaStream_t)s;
+    double *pivot_dev = packed + 2;
+    zonal_flags_kernel<<<1, 1, 0, st>>>(flags, pivot_dev, 0.0);
+    zonal_hash_reset_kernel<<<(cap + 255) / 256, 256, 0, st>>>((unsigned long long *)count, s1, s2, vmin, vmax, cap);
+    XRS_CUDA(cudaGetLastError());
+    ZhArgs a;
+    a.values = values; a.zones = zones; a.n = n; a.W = row_len; a.pivot = 0.0; a.pivot_ptr = nullptr;
+    a.zone_pivots = zone_pivots;
+    a.has_nodata = has_nodata; a.nodata = nodata;
+    a.keys = (long long *)keys;   // every key of this raster is already in the table: find-or-insert only finds
+    a.count = (unsigned long long *)count; a.s1 = s1; a.s2 = s2; a.vmin = vmin; a.vmax = vmax; a.cap = cap;
+    a.overflow = flags;
     int rc;
 #define XRS_ZH(VT)                                                               \
     switch (zones_dtype) {                                                       \

@@ -62,14 +62,15 @@ def _sample_pivot(values_t, comm=None):
 _MAX_OUT = 4096     # zones returned by the one-copy fast path of hash_partials
 
 
-def hash_partials(zones_t, values_t, nodata_values=None, comm=None, cap=1 << 16):
+def hash_partials(zones_t, values_t, nodata_values=None, comm=None, cap=1 << 16, table=None):
     """One streaming pass that discovers the zone ids and accumulates their partials
     (xrs_zonal_hash_run: pivot sampling, table init, accumulation and compaction are enqueued
     back to back; ONE device-to-host copy -- a 3-double header + 6 x 4096 doubles -- is the only
     synchronisation).  Returns (ids, part, pivot): ids = sorted unique finite zone values present
     in the raster (numpy, in the zones dtype), part = dict of numpy arrays aligned with ids
     (count int64; s1, s2, min, max float64), pivot = the scalar shift of s1/s2.
-    With `comm`, the tables of all ranks are merged by id (and share one pivot)."""
+    With `comm`, the tables of all ranks are merged by id (and share one pivot).
+    `table`: a dict that receives the device-side hash table (keys, cap) for `second_pass_partials`."""
     import torch
     dev = values_t.device
     hint = _sample_pivot(values_t, comm) if comm is not None else None
@@ -107,14 +108,76 @@ def hash_partials(zones_t, values_t, nodata_values=None, comm=None, cap=1 << 16)
     k = np.ascontiguousarray(rows[0]).view(np.int64)
     part = dict(count=np.ascontiguousarray(rows[1]).view(np.int64).copy(), s1=rows[2].copy(), s2=rows[3].copy(),
                 min=rows[4].copy(), max=rows[5].copy())
-    if zones_t.dtype.is_floating_point:
-        ids = k.view(np.float64).astype(np.float32 if zones_t.dtype == torch.float32 else np.float64)
-    else:
-        ids = k.astype(np.int32 if zones_t.dtype == torch.int32 else np.int64)
+    ids = _keys_to_ids(k, zones_t.dtype)
+    if table is not None:
+        table.update(keys=keys, cap=cap)
     if comm is not None:
         ids, part = allreduce_tables(ids, part, dev, comm)
     order = np.argsort(ids, kind="stable")
     return ids[order], {n: a[order] for n, a in part.items()}, pivot
+
+
+def _keys_to_ids(k, zones_dtype):
+    """int64 table keys -> zone ids in the zones' dtype (float zones: the key is the float64 bit pattern)"""
+    import torch
+    if zones_dtype.is_floating_point:
+        return k.view(np.float64).astype(np.float32 if zones_dtype == torch.float32 else np.float64)
+    return k.astype(np.int32 if zones_dtype == torch.int32 else np.int64)
+
+
+def second_pass_partials(zones_t, values_t, table, ids, means, nodata_values=None, comm=None):
+    """numpy's two-pass variance for float64 rasters: a second streaming pass over the hash table
+    `hash_partials(..., table=...)` left on the device, with the sums taken about every zone's own
+    mean (xrs_zonal_hash_second_pass; the means are scattered to the table's slots on the device, no
+    host round trip beyond the one the first pass needed).  `ids`: sorted zone ids (numpy), `means`:
+    float64, aligned -- over row stripes the merged ids / global means.  Returns the partials
+    (count, s1, s2, min, max about `means`) aligned with `ids`."""
+    import torch
+    dev = values_t.device
+    nz = len(ids)
+    part = dict(count=np.zeros(nz, np.int64), s1=np.zeros(nz), s2=np.zeros(nz),
+                min=np.full(nz, np.inf), max=np.full(nz, -np.inf))
+    if nz and values_t.numel():
+        keys, cap = table["keys"], table["cap"]
+        fz = zones_t.dtype.is_floating_point
+        ids_t = torch.as_tensor(np.asarray(ids, dtype=np.float64 if fz else np.int64), device=dev)
+        means_t = torch.as_tensor(np.asarray(means, dtype=np.float64), device=dev)
+        slot_ids = keys.view(torch.float64) if fz else keys
+        idx = torch.searchsorted(ids_t, slot_ids).clamp_(max=nz - 1)
+        pivots = means_t[idx].contiguous()                 # empty slots get some zone's mean: never read
+        blob = torch.empty((5, cap), dtype=torch.float64, device=dev)
+        packed = torch.empty(3 + 6 * _MAX_OUT, dtype=torch.float64, device=dev)
+        flags = torch.empty(2, dtype=torch.int32, device=dev)
+        count = blob[0].view(torch.int64)
+        P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+        with torch.cuda.device(dev):
+            _lib.call("xrs_zonal_hash_second_pass", P(values_t), _dtype_code(values_t), P(zones_t),
+                      _dtype_code(zones_t), values_t.numel(), int(values_t.shape[-1]) if values_t.dim() else 1,
+                      0 if nodata_values is None else 1, 0.0 if nodata_values is None else float(nodata_values),
+                      P(keys), P(pivots), P(count), P(blob[1]), P(blob[2]), P(blob[3]), P(blob[4]), cap,
+                      P(packed), _MAX_OUT, P(flags), stream_ptr(values_t))
+        host = packed.cpu().numpy()
+        n_used = int(host[0])
+        if n_used <= _MAX_OUT:
+            rows = host[3:].reshape(6, _MAX_OUT)[:, :n_used]
+        else:
+            used = torch.nonzero(keys != _EMPTY_KEY).reshape(-1)
+            rows = torch.cat([keys[used].view(torch.float64)[None], blob[:, used]]).cpu().numpy()
+        local = _keys_to_ids(np.ascontiguousarray(rows[0]).view(np.int64), zones_t.dtype)
+        pos = np.searchsorted(ids, local)
+        part["count"][pos] = np.ascontiguousarray(rows[1]).view(np.int64)
+        for i, n in enumerate(("s1", "s2", "min", "max")):
+            part[n][pos] = rows[2 + i]
+    if comm is not None and nz:
+        import torch.distributed as dist
+        t = {n: torch.as_tensor(a, device=dev) for n, a in part.items()}
+        dist.all_reduce(t["count"], op=dist.ReduceOp.SUM, group=comm)
+        dist.all_reduce(t["s1"], op=dist.ReduceOp.SUM, group=comm)
+        dist.all_reduce(t["s2"], op=dist.ReduceOp.SUM, group=comm)
+        dist.all_reduce(t["min"], op=dist.ReduceOp.MIN, group=comm)
+        dist.all_reduce(t["max"], op=dist.ReduceOp.MAX, group=comm)
+        part = {n: v.cpu().numpy() for n, v in t.items()}
+    return part
 
 
 class _PairTableOverflow(Exception):
@@ -138,7 +201,9 @@ def pair_counts(zones_t, values_t, nodata_values=None, comm=None, cap=1 << 20, m
         finite_zone = torch.isfinite(zones_t) if zones_t.dtype.is_floating_point else None
     else:
         zi, finite_zone = zones_t, None
-    vf = values_t.to(torch.float32) + 0.0              # -0.0 and 0.0 are one value (np.unique)
+    # float32 rasters are read in place (the kernel itself folds -0.0 into 0.0, one value for np.unique):
+    # a `+ 0.0` copy here cost a full extra read + write of the raster
+    vf = values_t if values_t.dtype == torch.float32 else values_t.to(torch.float32)
     if values_t.dtype != torch.float32 and not bool(((vf.to(values_t.dtype) == values_t) | ~torch.isfinite(values_t)).all()):
         raise NotImplementedError("'majority' needs values that are exact in float32")
     if finite_zone is not None:
@@ -384,7 +449,8 @@ def _stats_device(zones, values, zone_ids, stats_funcs, nodata_values, return_ty
     if len(vt.shape) > 2:
         raise TypeError('3D inputs not supported for the device backend')
     names = list(stats_funcs)
-    unique_zones, part_all, pivot0 = hash_partials(zt, vt, nodata_values, comm=comm)
+    table = {}
+    unique_zones, part_all, pivot0 = hash_partials(zt, vt, nodata_values, comm=comm, table=table)
     zdtype = unique_zones.dtype
     if zone_ids is None:
         sel = unique_zones
@@ -402,11 +468,14 @@ def _stats_device(zones, values, zone_ids, stats_funcs, nodata_values, return_ty
     if sv:
         if vt.dtype == torch.float64 and len(sel):
             # second pass about the per-zone means: numpy's two-pass variance, to ~1e-15
-            cnt = part["count"].astype(np.float64)
+            cnt = part_all["count"].astype(np.float64)
             with np.errstate(invalid="ignore", divide="ignore"):
-                means = np.where(cnt > 0, pivot + part["s1"] / cnt, 0.0)
-            part2, piv2 = zonal_partials(zt, vt, sel, nodata_values, pivot=means, comm=comm)
-            cols.update(finalize(part2, piv2, sv))
+                means = np.where(cnt > 0, pivot0 + part_all["s1"] / cnt, 0.0)
+            part2 = second_pass_partials(zt, vt, table, unique_zones, means, nodata_values, comm=comm)
+            if zone_ids is not None:
+                part2 = {n: a[pos] for n, a in part2.items()}
+                means = means[pos]
+            cols.update(finalize(part2, means, sv))
         else:
             cols.update(finalize(part, pivot, sv))
     if return_type == 'pandas.DataFrame':
@@ -641,7 +710,8 @@ def _crosstab_3d(zones, values, zone_ids, cat_ids, layer, agg, nodata_values, co
     for c in cats:
         lt = vt[cat_pos[c]].contiguous()
         lt = lt if lt.dtype in (torch.float32, torch.float64) else lt.to(torch.float64)
-        ids, part, pivot0 = hash_partials(zt, lt, nodata_values, comm=comm)
+        table = {}
+        ids, part, pivot0 = hash_partials(zt, lt, nodata_values, comm=comm, table=table)
         pos = np.searchsorted(ids, sel)
         pos = np.clip(pos, 0, max(len(ids) - 1, 0))
         hit = (ids[pos] == sel) if len(ids) else np.zeros(len(sel), bool)
@@ -651,8 +721,8 @@ def _crosstab_3d(zones, values, zone_ids, cat_ids, layer, agg, nodata_values, co
             cnt = part["count"].astype(np.float64)
             with np.errstate(invalid="ignore", divide="ignore"):
                 means = np.where(cnt > 0, pivot0 + part["s1"] / cnt, 0.0)
-            part2, piv2 = zonal_partials(zt, lt, ids, nodata_values, pivot=means, comm=comm)
-            col_all = finalize(part2, piv2, [agg])[agg]
+            part2 = second_pass_partials(zt, lt, table, ids, means, nodata_values, comm=comm)
+            col_all = finalize(part2, means, [agg])[agg]
         else:
             col_all = finalize(part, np.full(len(ids), pivot0), [agg])[agg]
         col = np.where(hit, col_all[pos] if len(ids) else np.nan, np.nan)
