@@ -229,7 +229,7 @@ int xrs_zonal_hash_run(const void *values, int values_dtype, const void *zones, 
  * read only -- with sums taken about `zone_pivots[slot]` (device, `cap` doubles: the zone's mean from the
  * first pass) instead of one global pivot, so that s2 / n - (s1 / n)^2 does not cancel.  count / s1 / s2 /
  * vmin / vmax: a second set of `cap`-entry accumulators (reset here); `packed` / `flags` as above
- * (packed[2] = 0).  Replaces the round-1 lookup-table kernel (xrs_zonal_partials_ex) on this path. */
+ * (packed[2] = 0).  values_dtype must be XRS_F64.  Replaces the round-1 lookup-table kernel (xrs_zonal_partials_ex) on this path. */
 int xrs_zonal_hash_second_pass(const void *values, int values_dtype, const void *zones, int zones_dtype, int64_t n,
                                int64_t row_len, int has_nodata, double nodata, const int64_t *keys,
                                const double *zone_pivots, int64_t *count, double *s1, double *s2, double *vmin,

@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/s2b_pytest.txt; tail -6 gpurun_out/s2b_pytest.txt
+timeout 900 python scripts/tune/box_sweep2.py 32768 > gpurun_out/s2b_box_sweep.txt 2>&1; tail -60 gpurun_out/s2b_box_sweep.txt

@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/s2e_pytest.txt; tail -6 gpurun_out/s2e_pytest.txt
+timeout 300 python scripts/bench_zonal.py > gpurun_out/s2e_bench_zonal.txt 2>&1; tail -8 gpurun_out/s2e_bench_zonal.txt
+timeout 600 python scripts/tune/box_sweep2.py 32768 > gpurun_out/s2e_sweep.txt 2>&1; tail -22 gpurun_out/s2e_sweep.txt

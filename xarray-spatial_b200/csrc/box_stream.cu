@@ -440,10 +440,10 @@ static int box_algo() {
     return (e && atoi(e) == 1) ? 1 : 2;
 }
 
-template <int RX> struct B2Shape {
+template <int RX, int NW> struct B2Shape {
     static constexpr int kPad = (RX + 3) / 4 * 4;               // columns a warp cannot emit on each side
     static constexpr int kOutW = kStripW - 2 * kPad;            // columns a warp emits
-    static constexpr int kTileOutW = kBsWarps * kOutW;
+    static constexpr int kTileOutW = NW * kOutW;
     static constexpr int kTileInW = kTileOutW + 2 * kPad;
     static constexpr int kNBox = (kTileInW + 255) / 256;
     static constexpr int kBoxW = ((kTileInW + kNBox - 1) / kNBox + 31) / 32 * 32;   // cells: 128-byte multiples
@@ -540,11 +540,11 @@ __device__ __forceinline__ void bs_lanesum(const T (&v)[R][4], T (&win)[R][4]) {
 
 __device__ __forceinline__ uint32_t bs_bits(int n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
 
-template <int RX>
-__global__ void __launch_bounds__((kBsWarps + 1) * 32, 2)
+template <int RX, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32, 2)
 box_stream2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ in, int64_t in_pitch_elems,
                    float *__restrict__ out, int64_t out_pitch_elems, const B2Geom g) {
-    using S = B2Shape<RX>;
+    using S = B2Shape<RX, NW>;
     constexpr int kw = 2 * RX + 1;
     constexpr int kStageCells = 2 * S::kHalfCells;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -556,7 +556,7 @@ box_stream2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__rest
         tma_prefetch_desc(&tmap);
         for (int s = 0; s < g.stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kBsWarps);
+            mbar_init(&empty[s], NW);
         }
         mbar_fence_init();
     }
@@ -565,7 +565,7 @@ box_stream2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__rest
     const int64_t n_tasks = (int64_t)g.n_tiles * g.n_segs;
     const int kh = g.kh, ry = g.ry;
 
-    if (warp == kBsWarps) {
+    if (warp == NW) {
         // ---- producer: per task the batches of 4 entering rows e0 .. e0 + 3 (row e = raster row
         // y0 - ry + e) and, once rows leave the window, the 4 rows e0 - (kh - 1) .. that leave with them
         if (lane == 0) {
@@ -738,31 +738,32 @@ box_stream2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__rest
     }
 }
 
-template <int RX>
+template <int RX, int NW>
 static int launch_box_stream2(const float *in, int64_t in_pitch, float *out, int64_t out_pitch, int64_t H, int64_t W,
                               int kh, double w, cudaStream_t s) {
-    using S = B2Shape<RX>;
+    using S = B2Shape<RX, NW>;
     CUtensorMap tmap;
     if (!make_tensor_map_2d(&tmap, in, in_pitch, H, W, 4, S::kBoxW, kB2Rows)) return kBoxNotTaken;
     B2Geom g;
     g.H = H; g.W = W; g.kh = kh; g.ry = kh / 2; g.w = w;
     g.n_tiles = (int)((W + S::kTileOutW - 1) / S::kTileOutW);
-    int stages = 3, max_ctas = 2, want = 4;
+    int stages = RX <= 2 ? 3 : 4, max_ctas = 2, want = 4;   // B200 sweep: profiles/r02s2_box_sweep.txt
     if (const char *e = getenv("XRS_BOX_STAGES")) stages = atoi(e);
     if (const char *e = getenv("XRS_BOX_CTAS")) max_ctas = atoi(e);
     if (const char *e = getenv("XRS_BOX_WAVES")) want = atoi(e);
     if (max_ctas < 1) max_ctas = 1;
     if (want < 1) want = 1;
     const size_t stage_bytes = (size_t)2 * S::kHalfBytes;
-    const size_t cap = (size_t)(224 * 1024) / max_ctas;
+    // shared memory of an SM: 228 KB, 1 KB of it reserved per resident CTA
+    const size_t cap = ((size_t)228 * 1024 - (size_t)max_ctas * 1024) / max_ctas - 256;
     if (stages < 2) stages = 2;
     while (stages > 2 && (size_t)stages * stage_bytes + (size_t)2 * stages * sizeof(uint64_t) > cap) --stages;
     g.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + (size_t)2 * stages * sizeof(uint64_t);
-    auto kern = box_stream2_kernel<RX>;
+    auto kern = box_stream2_kernel<RX, NW>;
     XRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (kBsWarps + 1) * 32, smem));
+    XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (NW + 1) * 32, smem));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > max_ctas) per_sm = max_ctas;
     const int64_t resident = (int64_t)sm_count() * per_sm;
@@ -773,8 +774,8 @@ static int launch_box_stream2(const float *in, int64_t in_pitch, float *out, int
     g.n_segs = (int)((H + seg_rows - 1) / seg_rows);
     const int64_t n_tasks = (int64_t)g.n_tiles * g.n_segs;
     const int64_t grid = resident < n_tasks ? resident : n_tasks;
-    kern<<<(unsigned)grid, (kBsWarps + 1) * 32, smem, s>>>(tmap, in, in_pitch / 4, out, out_pitch / 4, g);
-    last_launch_info() = {3, (int)grid, (kBsWarps + 1) * 32, (int)smem};
+    kern<<<(unsigned)grid, (NW + 1) * 32, smem, s>>>(tmap, in, in_pitch / 4, out, out_pitch / 4, g);
+    last_launch_info() = {3, (int)grid, (NW + 1) * 32, (int)smem};
     XRS_CUDA(cudaGetLastError());
     return XRS_OK;
 }
@@ -790,8 +791,13 @@ bool try_box_stream(const float *in, int64_t in_pitch, float *out, int64_t out_p
     if (W % 4 != 0 || out_pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(out) & 15)) return false;
     if (H >= (1LL << 31) - 64 || W >= (1LL << 31) - 4096) return false;
     if (box_algo() == 2) {
+        // 7 consumer warps + the producer = 256 threads: 128 registers per thread at two CTAs per SM (no
+        // spills; 8 + 1 warps are capped at 96 and spill in the fast path: 0.79 -> 0.87 of HBM at k = 9)
+        int nw = 7;
+        if (const char *e = getenv("XRS_BOX_WARPS")) nw = atoi(e);
         switch (kw / 2) {
-#define XRS_BS(R) case R: { const int r2 = launch_box_stream2<R>(in, in_pitch, out, out_pitch, H, W, kh, w, s); \
+#define XRS_BS(R) case R: { const int r2 = nw == 8 ? launch_box_stream2<R, 8>(in, in_pitch, out, out_pitch, H, W, kh, w, s)  \
+                                                     : launch_box_stream2<R, 7>(in, in_pitch, out, out_pitch, H, W, kh, w, s); \
                             if (r2 != kBoxNotTaken) { *rc = r2; return true; } } break;
             XRS_BS(1) XRS_BS(2) XRS_BS(3) XRS_BS(4) XRS_BS(5) XRS_BS(6) XRS_BS(7) XRS_BS(8) XRS_BS(9) XRS_BS(10) XRS_BS(11) XRS_BS(12)
 #undef XRS_BS

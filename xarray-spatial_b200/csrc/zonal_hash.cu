@@ -221,7 +221,8 @@ template <typename T> __device__ __forceinline__ ZhQuad<T> zh_load(const T *p, i
     return q;
 }
 
-template <typename VT, typename ZT>
+// ZP: sums about per-zone pivots (a.zone_pivots; the float64 second pass) instead of the one global pivot
+template <typename VT, typename ZT, bool ZP>
 __global__ void __launch_bounds__(kZhThreads, 3) zonal_hash_kernel(const __grid_constant__ ZhArgs a_in) {
     ZhArgs a = a_in;
     if (a.pivot_ptr != nullptr) a.pivot = *a.pivot_ptr;
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(kZhThreads, 3) zonal_hash_kernel(const __grid_
     ZT cur_z = ZT(0);
     bool have = false, cur_ok = false;
     long long cur_key = 0;
-    double cur_p = a.pivot;   // the shift of the lane's current run: global, or its zone's (second pass)
+    double cur_p = a.pivot;   // the shift of the lane's current run: global, or (ZP) its zone's
 
     // merge (key, cnt, s1, s2, mn, mx) into the CTA table, spilling to the global table when the
     // CTA sees more distinct zones than its table holds
@@ -356,34 +357,77 @@ __global__ void __launch_bounds__(kZhThreads, 3) zonal_hash_kernel(const __grid_
                     z[u] = zh_load<ZT>(zrow + u * a.W, 0, nvu, row_vec);
                 }
             }
+            // ---- the whole batch inside the lanes' current zones: one vote per 4 rows
+            bool all_same = have && batch_fast;
 #pragma unroll
+            for (int u = 0; u < kZhUnroll; ++u)
+                all_same = all_same && (z[u].v[0] == cur_z) && (z[u].v[1] == cur_z) && (z[u].v[2] == cur_z) &&
+                           (z[u].v[3] == cur_z);
+            if (__all_sync(0xffffffffu, all_same)) {
+                if (cur_ok) {
+#pragma unroll
+                    for (int u = 0; u < kZhUnroll; ++u) zh_add4<VT>(run, v[u].v, a, ZP ? cur_p : a.pivot);
+                }
+                continue;
+            }
+            // ---- otherwise ONE copy of the row code walks the batch (it used to be unrolled four times,
+            // with the flush code inlined in each: on irregular zones the kernel's top stall was
+            // `no_instruction`, 6 cycles per issued instruction -- instruction-cache misses)
+            static_assert(kZhUnroll == 4, "the row pick below is written for 4 rows");
+#pragma unroll 1
             for (int u = 0; u < kZhUnroll; ++u) {
+                const ZhQuad<VT> vq = u == 0 ? v[0] : (u == 1 ? v[1] : (u == 2 ? v[2] : v[3]));
+                const ZhQuad<ZT> zq = u == 0 ? z[0] : (u == 1 ? z[1] : (u == 2 ? z[2] : z[3]));
                 const int nvu = batch_fast ? 4 : ((y + u < y1) ? nv : 0);
-                const bool same = have && (z[u].v[0] == cur_z) && (z[u].v[1] == cur_z) &&
-                                  (z[u].v[2] == cur_z) && (z[u].v[3] == cur_z);
+                const bool same = have && (zq.v[0] == cur_z) && (zq.v[1] == cur_z) && (zq.v[2] == cur_z) &&
+                                  (zq.v[3] == cur_z);
                 const bool fast = (nvu == 4) && same;
                 if (!__all_sync(0xffffffffu, fast || nvu == 0)) {
-                    // some lane meets a zone boundary (or a ragged right edge): cell by cell,
-                    // every lane taking part in every (collective) flush
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const bool live = k < nvu;
-                        const ZT zk = z[u].v[k];
-                        const bool change = live && (!have || !(zk == cur_z));
-                        if (__any_sync(0xffffffffu, change)) flush_all(change && have);
-                        if (change) {
-                            cur_z = zk;
-                            have = (zk == zk);
-                            cur_ok = zh_key<ZT>(zk, cur_key);
-                            if (a.zone_pivots != nullptr && cur_ok) {
+                    // Some lane meets a zone boundary (or a ragged right edge).  A boundary between two
+                    // raster ROWS reaches every lane at the row's first cell: that cell is handled with the
+                    // collective flush (all 32 lanes take part; lanes leaving the same zone combine their
+                    // runs by shuffles).  A boundary between two COLUMNS wanders through single lanes: the
+                    // other three cells are each lane's own business -- no votes, no shuffles, a lane that
+                    // changes zone flushes its own run (round 2 voted once per cell of such a row).
+                    auto enter = [&](ZT zk) {
+                        cur_z = zk;
+                        have = (zk == zk);
+                        cur_ok = zh_key<ZT>(zk, cur_key);
+                        if constexpr (ZP) {
+                            if (cur_ok) {
                                 const int ps = zh_find(a.keys, a.cap, cur_key);
                                 cur_p = ps >= 0 ? a.zone_pivots[ps] : a.pivot;
                             }
                         }
-                        if (live && cur_ok) zh_add<VT>(run, v[u].v[k], a, cur_p);
+                    };
+                    {
+                        const bool live = 0 < nvu;
+                        const ZT zk = zq.v[0];
+                        const bool change = live && (!have || !(zk == cur_z));
+                        if (__any_sync(0xffffffffu, change)) flush_all(change && have);
+                        if (change) enter(zk);
+                        if (live && cur_ok) zh_add<VT>(run, vq.v[0], a, ZP ? cur_p : a.pivot);
                     }
+#pragma unroll 1
+                    for (int k = 1; k < 4; ++k) {
+                        if (k < nvu) {
+                            const ZT zk = k == 1 ? zq.v[1] : (k == 2 ? zq.v[2] : zq.v[3]);
+                            const VT vk = k == 1 ? vq.v[1] : (k == 2 ? vq.v[2] : vq.v[3]);
+                            if (!have || !(zk == cur_z)) {
+                                if (have && cur_ok) {
+                                    const double mn = sizeof(VT) == 4 ? (double)run.mnf : run.mnd;
+                                    const double mx = sizeof(VT) == 4 ? (double)run.mxf : run.mxd;
+                                    merge(cur_key, run.cnt, run.s1, run.s2, mn, mx);
+                                    zh_reset<VT>(run);
+                                }
+                                enter(zk);
+                            }
+                            if (cur_ok) zh_add<VT>(run, vk, a, ZP ? cur_p : a.pivot);
+                        }
+                    }
+                    __syncwarp();
                 } else if (fast && cur_ok) {
-                    zh_add4<VT>(run, v[u].v, a, cur_p);
+                    zh_add4<VT>(run, vq.v, a, ZP ? cur_p : a.pivot);
                 }
             }
         }
@@ -436,40 +480,40 @@ __global__ void __launch_bounds__(kZhThreads) zonal_pair_kernel(const __grid_con
     __syncthreads();
     const bool al = ((reinterpret_cast<uintptr_t>(a.values) | reinterpret_cast<uintptr_t>(a.zones)) & 15) == 0 &&
                     (a.W % 4 == 0);
-    long long cur_key = kZhEmpty;
-    unsigned run = 0u;
-    auto merge = [&](long long key, unsigned cnt) {
+    // Every lane keeps TWO open runs (zone, value, count): class boundaries on a real categorical raster
+    // are noisy -- a lane walking down its 4 columns flips between the two classes either side of a
+    // boundary many times before it leaves it behind -- so a single run was flushed at every flip (round
+    // 2: a vote and a shuffle per cell of such a row, 43 instructions per cell, ALU pipe 64 % busy, 0.25
+    // of the HBM roofline on the banded benchmark DEM).  Now:
+    //   * clean batch (one vote per 4 rows): every cell of every lane lies in the lane's zone and holds
+    //     one of the lane's two values -> per cell two float compares and two adds, nothing else (an
+    //     invalid cell -- NaN, inf, nodata -- matches neither value, so validity needs no test here);
+    //   * anything else: ONE copy of the generic per-lane code walks the batch's rows cell by cell; a third
+    //     pair evicts the run used less recently.  No votes, no shuffles: a flush is the lane's own
+    //     business (native 32-bit shared-memory atomics), and the code stays small enough for the
+    //     instruction cache (ncu of the unrolled version: `no_instruction` among the top stalls).
+    int zone0 = 0, zone1 = 0;
+    float v0 = nan_of<float>(), v1 = nan_of<float>();   // NaN never matches: the runs start empty
+    unsigned c0 = 0u, c1 = 0u;
+    bool last1 = false;      // the run used most recently is run 1
+    auto merge = [&](int zone, float val, unsigned cnt) {
+        const long long key = ((long long)zone << 32) | (long long)__float_as_uint(val);
         int s = zh_slot(s_keys, kCap, key, 64);
         if (s >= 0) { atomicAdd(&s_cnt[s], cnt); return; }
         s = zh_slot(a.keys, a.cap, key, a.cap);
         if (s < 0) *a.overflow = 1; else atomicAdd(&a.count[s], (unsigned long long)cnt);
     };
-    auto flush_all = [&](bool need) {
-        const unsigned full = 0xffffffffu;
-        need = need && run != 0u;
-        const long long key0 = __shfl_sync(full, cur_key, 0);
-        if (__all_sync(full, need && cur_key == key0)) {
-            const unsigned cnt = __reduce_add_sync(full, run);
-            if ((threadIdx.x & 31) == 0) merge(key0, cnt);
-        } else if (need) {
-            merge(cur_key, run);
-        }
-        __syncwarp();
-        if (need) run = 0u;
-    };
     const int lane = threadIdx.x & 31;
     const int64_t H = a.n / a.W;
     const int64_t n_strips = (a.W + 127) / 128, n_segs = (H + kZhSegRows - 1) / kZhSegRows;
     const int64_t warps_total = (int64_t)gridDim.x * (kZhThreads / 32);
+    static_assert(kZhUnroll == 4, "the row pick below is written for 4 rows");
     for (int64_t task = (int64_t)blockIdx.x * (kZhThreads / 32) + (threadIdx.x >> 5); task < n_strips * n_segs;
          task += warps_total) {
         const int64_t seg = task / n_strips, strip = task % n_strips;
         const int64_t x = strip * 128 + 4 * lane;
         const int64_t y0 = seg * kZhSegRows, y1 = min(y0 + (int64_t)kZhSegRows, H);
         const int nv = (int)max((int64_t)0, min((int64_t)4, a.W - x));
-        // kZhUnroll rows of 128-bit loads in flight per lane (the row-at-a-time version of round 1 sat at
-        // 0.23-0.26 of the HBM roofline, waiting on one load pair per iteration), and a vote-only fast path
-        // for rows in which no lane meets a new (zone, value) pair
         for (int64_t y = y0; y < y1; y += kZhUnroll) {
             ZhQuad<float> v[kZhUnroll];
             ZhQuad<int> z[kZhUnroll];
@@ -480,35 +524,60 @@ __global__ void __launch_bounds__(kZhThreads) zonal_pair_kernel(const __grid_con
                 v[u] = zh_load<float>(a.values, i0, i0 + nvu, al);
                 z[u] = zh_load<int>(a.zones, i0, i0 + nvu, al);
             }
+            // ---- clean batch?
+            const bool full_batch = (nv == 4) && (y + kZhUnroll <= y1);
+            const int zc = last1 ? zone1 : zone0;          // the zone of the run used last
+            unsigned m0 = 0u, m1 = 0u;
+            int zdiff = 0;
 #pragma unroll
             for (int u = 0; u < kZhUnroll; ++u) {
-                const int nvu = (y + u < y1) ? nv : 0;
-                bool ok[4], change = false;
-                long long key[4];
-                unsigned n_ok = 0u;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const float f = v[u].v[k] + 0.0f;  // -0.0 -> +0.0
-                    ok[k] = k < nvu && (fabsf(f) <= 3.402823466e38f) && !(a.has_nodata && f == a.nodata);
-                    key[k] = ((long long)z[u].v[k] << 32) | (long long)__float_as_uint(f);
-                    change = change || (ok[k] && key[k] != cur_key);
-                    n_ok += ok[k] ? 1u : 0u;
-                }
-                if (!__any_sync(0xffffffffu, change)) {
-                    run += n_ok;         // every valid cell of every lane continues its lane's run
-                    continue;
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const bool ch = ok[k] && key[k] != cur_key;
-                    if (__any_sync(0xffffffffu, ch)) flush_all(ch);
-                    if (ch) cur_key = key[k];
-                    if (ok[k]) run += 1u;
+                    zdiff |= z[u].v[k] ^ zc;
+                    m0 += (v[u].v[k] == v0) ? 1u : 0u;
+                    m1 += (v[u].v[k] == v1) ? 1u : 0u;
                 }
             }
+            if (zone0 != zc) m0 = 0u;      // a run left over from another zone takes no part
+            if (zone1 != zc) m1 = 0u;
+            const bool clean = full_batch && zdiff == 0 && (m0 + m1 == 4u * kZhUnroll);
+            if (__all_sync(0xffffffffu, clean || nv == 0)) {
+                if (nv != 0) {
+                    c0 += m0;
+                    c1 += m1;
+                    last1 = (zone1 == zc) && (v[kZhUnroll - 1].v[3] == v1);
+                }
+                continue;
+            }
+            // ---- generic: row by row, cell by cell, every lane on its own
+#pragma unroll 1
+            for (int u = 0; u < kZhUnroll; ++u) {
+                const ZhQuad<float> vq = u == 0 ? v[0] : (u == 1 ? v[1] : (u == 2 ? v[2] : v[3]));
+                const ZhQuad<int> zq = u == 0 ? z[0] : (u == 1 ? z[1] : (u == 2 ? z[2] : z[3]));
+                const int nvu = (y + u < y1) ? nv : 0;
+#pragma unroll 1
+                for (int k = 0; k < 4; ++k) {
+                    if (k >= nvu) break;
+                    const float fr = k == 0 ? vq.v[0] : (k == 1 ? vq.v[1] : (k == 2 ? vq.v[2] : vq.v[3]));
+                    const int zk = k == 0 ? zq.v[0] : (k == 1 ? zq.v[1] : (k == 2 ? zq.v[2] : zq.v[3]));
+                    const float f = fr + 0.0f;  // -0.0 -> +0.0: one value for np.unique
+                    if (!(fabsf(f) <= 3.402823466e38f) || (a.has_nodata && f == a.nodata)) continue;
+                    if (zk == zone0 && f == v0) { c0 += 1u; last1 = false; }
+                    else if (zk == zone1 && f == v1) { c1 += 1u; last1 = true; }
+                    else if (last1) {            // evict run 0
+                        if (c0 != 0u) merge(zone0, v0, c0);
+                        zone0 = zk; v0 = f; c0 = 1u; last1 = false;
+                    } else {                     // evict run 1
+                        if (c1 != 0u) merge(zone1, v1, c1);
+                        zone1 = zk; v1 = f; c1 = 1u; last1 = true;
+                    }
+                }
+            }
+            __syncwarp();
         }
     }
-    flush_all(true);
+    if (c0 != 0u) merge(zone0, v0, c0);
+    if (c1 != 0u) merge(zone1, v1, c1);
     __syncthreads();
     for (int i = threadIdx.x; i < kCap; i += blockDim.x) {
         if (s_keys[i] != kZhEmpty && s_cnt[i]) {
@@ -594,19 +663,19 @@ __global__ void zonal_flags_kernel(int *flags, double *pivot_dev, double pivot_h
     if (pivot_dev) *pivot_dev = pivot_hint;
 }
 
-template <typename VT, typename ZT> static int launch_zh(const ZhArgs &a, cudaStream_t s) {
+template <typename VT, typename ZT, bool ZP = false> static int launch_zh(const ZhArgs &a, cudaStream_t s) {
     const int64_t H = a.n / a.W;
     const int64_t n_tasks = ((a.W + 127) / 128) * ((H + kZhSegRows - 1) / kZhSegRows);
     constexpr size_t smem = ZhTable<VT>::kBytes;
-    XRS_CUDA(cudaFuncSetAttribute(zonal_hash_kernel<VT, ZT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    XRS_CUDA(cudaFuncSetAttribute(zonal_hash_kernel<VT, ZT, ZP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zonal_hash_kernel<VT, ZT>, kZhThreads, smem));
+    XRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zonal_hash_kernel<VT, ZT, ZP>, kZhThreads, smem));
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)sm_count() * per_sm;
     const int64_t need = (n_tasks + kZhThreads / 32 - 1) / (kZhThreads / 32);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    zonal_hash_kernel<VT, ZT><<<(unsigned)grid, kZhThreads, smem, s>>>(a);
+    zonal_hash_kernel<VT, ZT, ZP><<<(unsigned)grid, kZhThreads, smem, s>>>(a);
     XRS_CUDA(cudaGetLastError());
     return XRS_OK;
 }
@@ -707,7 +776,7 @@ int xrs_zonal_hash_second_pass(const void *values, int values_dtype, const void 
                                double *vmax, int cap, double *packed, int max_out, int *flags, xrs_stream_t s) {
     XRS_REQUIRE(values && zones && keys && zone_pivots && count && s1 && s2 && vmin && vmax && packed && flags,
                 "NULL pointer");
-    XRS_REQUIRE(values_dtype == XRS_F32 || values_dtype == XRS_F64, "values must be float32 or float64");
+    XRS_REQUIRE(values_dtype == XRS_F64, "the second pass is for float64 values");
     XRS_REQUIRE(zones_dtype >= XRS_F32 && zones_dtype <= XRS_I64, "unknown zones dtype");
     XRS_REQUIRE(cap >= 1024 && (cap & (cap - 1)) == 0, "cap must be a power of two >= 1024");
     XRS_REQUIRE(max_out >= 1, "max_out must be positive");
@@ -725,15 +794,12 @@ int xrs_zonal_hash_second_pass(const void *values, int values_dtype, const void 
     a.count = (unsigned long long *)count; a.s1 = s1; a.s2 = s2; a.vmin = vmin; a.vmax = vmax; a.cap = cap;
     a.overflow = flags;
     int rc;
-#define XRS_ZH(VT)                                                               \
-    switch (zones_dtype) {                                                       \
-        case XRS_I32: rc = launch_zh<VT, int>(a, st); break;                     \
-        case XRS_I64: rc = launch_zh<VT, long long>(a, st); break;               \
-        case XRS_F32: rc = launch_zh<VT, float>(a, st); break;                   \
-        default: rc = launch_zh<VT, double>(a, st); break;                       \
+    switch (zones_dtype) {
+        case XRS_I32: rc = launch_zh<double, int, true>(a, st); break;
+        case XRS_I64: rc = launch_zh<double, long long, true>(a, st); break;
+        case XRS_F32: rc = launch_zh<double, float, true>(a, st); break;
+        default: rc = launch_zh<double, double, true>(a, st); break;
     }
-    if (values_dtype == XRS_F32) { XRS_ZH(float) } else { XRS_ZH(double) }
-#undef XRS_ZH
     if (rc != XRS_OK) return rc;
     zonal_compact_kernel<<<(cap + 255) / 256, 256, 0, st>>>((const long long *)keys, (const unsigned long long *)count,
                                                            s1, s2, vmin, vmax, cap, packed, max_out, flags);
