@@ -591,6 +591,13 @@ def run_ops_record(xb, stripes, attrs, args, peak, dist, dev):
             add("convolve_2d k=%d %s" % (k, kind), event_times(lambda: convolve_2d(sub, kern), max(3, steps // 2))[0], 8,
                 float(sub.shape[0]) * W, p,
                 "f64 accumulation like the reference; bound: HBM (k=3, uniform) or the FP64 FMA rate (mixed k>=9)")
+    # the reference's own focal benchmark (benchmarks/benchmarks/focal.py FocalApply): apply(agg, np.ones((k, k)))
+    from xrspatial_b200 import focal as xfocal
+    for k in (5, 25):
+        kern = np.ones((k, k))
+        p = par(xfocal.apply(wagg, kern).data, oracle.focal_apply(hwin, kern, "mean", nthreads=th))
+        add("focal.apply mean, np.ones((%d, %d))" % (k, k), event_times(lambda: xfocal.apply(agg, kern), max(3, steps // 2))[0],
+            8, cells, p, "running box in NaN-skipping mode (clamped windows at the raster's edges)")
     # config 4 with the reference's default list (incl. majority) on a categorical raster
     cats = (stripes.interior * (16.0 / 4000.0)).floor_().clamp_(0, 15)
     cagg = xb.DataArray(cats, dims=("y", "x"))

@@ -167,35 +167,17 @@ int xrs_ebbi_f32(const float *red, const float *swir, const float *tir, float *o
                  xrs_stream_t s);
 
 /* ------------------------------------------------------------------ zonal.stats
- * zonal._stats_cupy (zonal.py:335-419) / `_stats_numpy` (:280-332) replaced by one scan that
- * accumulates per-zone partials; mean/std/var are finalised from them by the caller, and
- * partials from several devices combine with sum / min / max (NCCL AllReduce).
+ * zonal._stats_cupy (zonal.py:335-419) / `_stats_numpy` (:280-332) replaced by one streaming group-by that
+ * discovers the zone ids and accumulates per-zone partials; mean / std / var are finalised from them by the
+ * caller, and partials from several devices combine with sum / min / max (NCCL AllReduce).  (Round 1 also
+ * exported a lookup-table kernel for a given id list, xrs_zonal_partials(_ex): 0.24 of the HBM roofline,
+ * slower than the group-by it specialised; removed -- the float64 second pass now runs on the group-by
+ * kernel, xrs_zonal_hash_second_pass.)
  *
- * zones (zones_dtype: I32, I64, F32, F64) and values (values_dtype: F32, F64, I32, I64) are
- * device arrays of n cells.  `zone_ids` is a DEVICE array of nz sorted unique ids as float64;
- * a cell contributes to the zone whose id equals its zone value, if its value is finite and
- * != nodata (when has_nodata).  Outputs (device, length nz, caller-zeroed/initialised by
- * xrs_zonal_init): count (int64), sum, sumsq of (v - pivot[z]) (float64), min, max
- * (float64).  pivot is a DEVICE float64 array of nz (a per-zone shift, any finite value in
- * the zone's range; identical on all devices) that keeps sumsq well conditioned. */
-int xrs_zonal_init(int64_t *count, double *sum, double *sumsq, double *vmin, double *vmax,
-                   int nz, xrs_stream_t s);
-int xrs_zonal_partials(const void *values, int values_dtype, const void *zones,
-                       int zones_dtype, int64_t n, const double *zone_ids, int nz,
-                       const double *pivot, int has_nodata, double nodata, int64_t *count,
-                       double *sum, double *sumsq, double *vmin, double *vmax,
-                       xrs_stream_t s);
-/* same, with a hint for integer zone rasters whose ids all lie in
- * [lut_base, lut_base + 8192): use_lut != 0 replaces the binary search of zone_ids by a
- * direct shared-memory table.  row_len = raster row length (n = rows * row_len), see
- * xrs_zonal_hash_accumulate. */
-int xrs_zonal_partials_ex(const void *values, int values_dtype, const void *zones,
-                          int zones_dtype, int64_t n, const double *zone_ids, int nz,
-                          const double *pivot, int has_nodata, double nodata, int use_lut,
-                          int64_t lut_base, int64_t row_len, int64_t *count, double *sum,
-                          double *sumsq, double *vmin, double *vmax, xrs_stream_t s);
+ * zones (zones_dtype: I32, I64, F32, F64) and values (values_dtype: F32, F64) are device arrays of n
+ * cells; a cell contributes to its zone if its value is finite and != nodata (when has_nodata). */
 
-/* Single-pass variant that DISCOVERS the zone ids: group-by aggregation into an open-addressing
+/* The group-by: aggregation into an open-addressing
  * hash table of `cap` slots (power of two >= 1024; device arrays keys/count/s1/s2/vmin/vmax of
  * `cap` entries, initialised by xrs_zonal_hash_init).  keys[slot] is the zone id (int64 for
  * integer zones, the bit pattern of the float64 value for float zones; INT64_MIN = empty),
@@ -229,7 +211,7 @@ int xrs_zonal_hash_run(const void *values, int values_dtype, const void *zones, 
  * read only -- with sums taken about `zone_pivots[slot]` (device, `cap` doubles: the zone's mean from the
  * first pass) instead of one global pivot, so that s2 / n - (s1 / n)^2 does not cancel.  count / s1 / s2 /
  * vmin / vmax: a second set of `cap`-entry accumulators (reset here); `packed` / `flags` as above
- * (packed[2] = 0).  values_dtype must be XRS_F64.  Replaces the round-1 lookup-table kernel (xrs_zonal_partials_ex) on this path. */
+ * (packed[2] = 0).  values_dtype must be XRS_F64.  */
 int xrs_zonal_hash_second_pass(const void *values, int values_dtype, const void *zones, int zones_dtype, int64_t n,
                                int64_t row_len, int has_nodata, double nodata, const int64_t *keys,
                                const double *zone_pivots, int64_t *count, double *s1, double *s2, double *vmin,

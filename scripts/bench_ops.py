@@ -110,8 +110,6 @@ zt, vt = zones, dem
 sel = np.arange(1024, dtype=np.int32)
 add("zonal hash partials (ids discovered)", timeit(lambda: Z.hash_partials(zt, vt)), 8,
     note="xrs_zonal_hash_accumulate + compaction + tiny D2H")
-add("zonal partials, ids given (LUT)", timeit(lambda: Z.zonal_partials(zt, vt, sel), n=3), 8,
-    note="xrs_zonal_partials_ex")
 hz = ((torch.arange(side, device="cuda", dtype=torch.int64)[:, None] * 7919 +
        torch.arange(side, device="cuda", dtype=torch.int64)[None, :] * 104729) % 1024).to(torch.int32)
 add("zonal hash partials, scattered zones", timeit(lambda: Z.hash_partials(hz, vt), n=3), 8,

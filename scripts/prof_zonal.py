@@ -15,7 +15,6 @@ zones = (yy * 32 + xx).contiguous()
 sel = np.arange(1024, dtype=np.int32)
 for _ in range(2):
     Z.hash_partials(zones, t)
-    Z.zonal_partials(zones, t, sel)
     convolve_2d(t[: side // 4], np.ones((9, 9)) / 81.0)
     xb.aspect(xb.DataArray(t))
 torch.cuda.synchronize()

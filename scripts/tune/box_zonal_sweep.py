@@ -1,7 +1,9 @@
-"""A/B of the two running-box kernels (XRS_BOX_ALGO=1: prefix scan, window in the ring; 2: lane sums,
-two-stream stages) and a sweep of the second one's knobs on one GPU.
+"""Sweep of the running-box kernel's knobs (XRS_BOX_STAGES, XRS_BOX_CTAS, XRS_BOX_WAVES) on one GPU, then the
+zonal kernels on block / noisy zones and the float64 two-pass statistics.
 usage: box_sweep2.py [side]  -> ms / Gcells/s / fraction of the measured copy peak per configuration;
-outputs are compared with the first configuration of each k (max |diff| relative to max |ref|)."""
+outputs are compared with the first configuration of each k (max |diff| relative to max |ref|).
+(profiles/r02s2_box_sweep_*.txt were written by earlier versions of this script that could also switch to
+the first-generation kernel, XRS_BOX_ALGO=1, and to 8 / 9 consumer warps, XRS_BOX_WARPS.)"""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
@@ -15,13 +17,12 @@ PEAK = 6569.6
 t = torch.empty((side, side), dtype=torch.float32, device="cuda")
 _lib.call("xrs_synth_terrain_f32", ctypes.c_void_p(t.data_ptr()), side * 4, side, side, 0, 0, 1235, 0.0, 4000.0,
           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-cfgs = [("2", None, None, None, None)]
+cfgs = [(None, None, None), (3, 2, 4), (4, 2, 4), (3, 2, 8), (4, 2, 8), (4, 1, 4)]
 for k in (5, 9, 15, 25):
     kern = np.ones((k, k)) / (k * k)
     ref = None
-    for algo, stages, ctas, waves, warps in cfgs:
-        os.environ["XRS_BOX_ALGO"] = algo
-        for name, val in (("XRS_BOX_STAGES", stages), ("XRS_BOX_CTAS", ctas), ("XRS_BOX_WAVES", waves), ("XRS_BOX_WARPS", warps)):
+    for stages, ctas, waves in cfgs:
+        for name, val in (("XRS_BOX_STAGES", stages), ("XRS_BOX_CTAS", ctas), ("XRS_BOX_WAVES", waves)):
             if val is None:
                 os.environ.pop(name, None)
             else:
@@ -42,10 +43,10 @@ for k in (5, 9, 15, 25):
             fin = torch.isfinite(ref)
             same_mask = bool(torch.equal(torch.isnan(out), torch.isnan(ref)))
             diff = "%.2e nanmask=%s" % (float((out[fin] - ref[fin]).abs().max() / ref[fin].abs().max()), same_mask)
-        print("k=%2d algo=%s stages=%s ctas<=%s waves=%s warps=%s : %.3f ms  %.1f Gcells/s  frac %.3f  diff=%s" %
-              (k, algo, stages, ctas, waves, warps, ms, side * side / ms / 1e6, side * side * 8 / ms / 1e6 / PEAK, diff), flush=True)
+        print("k=%2d stages=%s ctas<=%s waves=%s : %.3f ms  %.1f Gcells/s  frac %.3f  diff=%s" %
+              (k, stages, ctas, waves, ms, side * side / ms / 1e6, side * side * 8 / ms / 1e6 / PEAK, diff), flush=True)
         del out
-for name in ("XRS_BOX_ALGO", "XRS_BOX_STAGES", "XRS_BOX_CTAS", "XRS_BOX_WAVES", "XRS_BOX_WARPS"):
+for name in ("XRS_BOX_STAGES", "XRS_BOX_CTAS", "XRS_BOX_WAVES"):
     os.environ.pop(name, None)
 
 # the (zone, value) pair histogram behind `majority` / `crosstab`, and the default zonal.stats call
@@ -79,23 +80,7 @@ _lib.call("xrs_synth_terrain_f32", ctypes.c_void_p(t2.data_ptr()), side * 4, sid
 zirr = (t2 * (64.0 / 4000.0)).floor_().clamp_(0, 63).to(torch.int32)
 del t2
 
-
-def smooth_zones(side, seed=5):
-    """~1000 zones with smooth, irregular outlines (rasterised-polygon-like): two coarse random fields,
-    bilinearly upsampled, 32 contour bands each"""
-    import torch.nn.functional as F
-    gen = torch.Generator(device="cuda").manual_seed(seed)
-    out = torch.zeros((side, side), dtype=torch.int32, device="cuda")
-    for mul in (1, 32):
-        coarse = torch.rand((1, 1, 48, 48), generator=gen, device="cuda")
-        fine = F.interpolate(coarse, size=(side, side), mode="bicubic", align_corners=True)[0, 0]
-        out += (fine.clamp_(0, 0.999) * 32).to(torch.int32) * mul
-        del fine
-    return out
-
-
-zvor = smooth_zones(side)
-for name, zz in (("block zones", zones), ("smooth irregular zones (~1000 polygons)", zvor), ("noisy zones (64 contour bands of a rough fBm surface)", zirr)):
+for name, zz in (("block zones", zones), ("noisy zones (64 contour bands of a rough fBm surface)", zirr)):
     for _ in range(2):
         Z.hash_partials(zz, t)
     torch.cuda.synchronize()

@@ -21,7 +21,7 @@ def test_header_declares_the_hot_path():
     for s in ("xrs_slope_f32", "xrs_aspect_f32", "xrs_curvature_f32", "xrs_hillshade_f32",
               "xrs_surface_suite_f32", "xrs_focal_mean_f32", "xrs_focal_mean_f64", "xrs_convolve2d_f32",
               "xrs_focal_stat_f32", "xrs_normalized_ratio_f32", "xrs_savi_f32", "xrs_evi_f32",
-              "xrs_zonal_partials", "xrs_host_stencil"):
+              "xrs_zonal_hash_run", "xrs_zonal_hash_second_pass", "xrs_host_stencil"):
         assert s in syms
 
 

@@ -1014,6 +1014,39 @@ def test_streaming_box_convolve_many_tiles_and_sentinels(xb, k):
         assert_close_f32(got, ref, atol=1e-6 * np.nanmax(np.abs(ref)), what="box %dx%d" % (kh, kw))
 
 
+@pytest.mark.parametrize("kh,kw", [(5, 5), (25, 25), (3, 7), (9, 3), (1, 5), (15, 15)])
+def test_focal_apply_mean_over_all_ones_windows_takes_the_running_box(xb, kh, kw):
+    """focal.apply(raster, np.ones((kh, kw))) -- the reference's own focal benchmark (benchmarks/focal.py
+    FocalApply) -- runs on the running-box kernel in NaN-skipping mode: NaN cells and cells beyond the raster
+    are skipped (clamped windows at the edges), infinite cells take part, an all-NaN window is NaN
+    (focal.py:268-270, 305-326)."""
+    from xrspatial_b200 import focal
+    rng = np.random.default_rng(7000 + 31 * kh + kw)
+    z = terrain(rng, 1300, 2052)                      # several CTA tiles and row segments
+    kern = np.ones((kh, kw))
+    got = host(focal.apply(da(xb, dev(z)), kern))
+    assert used_tma(xb) == 3
+    assert_close_f32(got, o.focal_apply(z, kern, "mean", nthreads=16), what="apply mean %dx%d clean" % (kh, kw))
+    d = z.copy()
+    d[rng.random(d.shape) < 0.002] = np.nan
+    d[200:240, 300:340] = np.nan                      # all-NaN windows (for the smaller kernels)
+    d[700, 1000] = np.inf
+    d[900, 40] = -np.inf
+    d[1100:1103, 2000:2003] = np.float32(3.4028235e38)
+    ref = o.focal_apply(d, kern, "mean", nthreads=16)
+    got = host(focal.apply(da(xb, dev(d)), kern))
+    assert used_tma(xb) == 3
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
+    fin = np.isfinite(ref) & (np.abs(ref) < 1e20)
+    assert_close_f32(np.where(fin, got, 0), np.where(fin, ref, 0), what="apply mean %dx%d, ordinary windows" % (kh, kw))
+    odd = ~np.isnan(ref) & ~fin
+    assert odd.any()
+    np.testing.assert_allclose(got[odd], ref[odd], rtol=1e-6)      # infinite / huge windows: the reference's order
+    # the other reducers and kernels with holes keep the tiled kernel
+    focal.apply(da(xb, dev(z[:200, :256])), kern, func="sum")
+    assert used_tma(xb) != 3
+
+
 def test_crosstab_3d(xb, known, refout):
     """zonal.py:1096-1116 / :734-745: 3-D `values`, categories = coordinate of dimension `layer`, cell =
     statistic `agg` of the layer over the zone.  The reference's own fixtures (test_zonal.py:48-58,

@@ -266,6 +266,27 @@ def test_focal_mean_division_by_count_is_correctly_rounded():
     assert bad == 0
 
 
+def test_running_box_mean_division_by_the_window_size_is_correctly_rounded():
+    """bs_div_n (box_stream.cu, NaN-skipping mode = focal.apply mean over an all-ones window): the window sum
+    divided by kh * kw as q = c * (1/n), q + fma(-q, n, c) * (1/n), for every window size the kernel serves
+    (odd kh, kw <= 25).  With exact FMAs (rationals) that is the correctly rounded float64 quotient np.nanmean
+    forms, so the float32 result cannot depend on which of the kernel's paths produced it."""
+    from fractions import Fraction
+    rng = np.random.default_rng(25)
+    vals = np.concatenate([rng.standard_normal(300) * 10.0 ** rng.integers(-6, 9, 300),
+                           rng.uniform(0, 4000 * 625, 300), [0.0, 1.0, 4000.0 * 625, 1e-300, 1e300]])
+    sizes = sorted({kh * kw for kh in range(1, 26, 2) for kw in range(3, 26, 2)})
+    bad = 0
+    for c in vals:
+        for n in sizes:
+            inv = 1.0 / n
+            q = c * inv
+            r = float(Fraction(c) - Fraction(q) * n)               # fma(-q, n, c): one rounding
+            res = float(Fraction(r) * Fraction(inv) + Fraction(q))  # fma(r, inv, q): one rounding
+            bad += res != c / n
+    assert bad == 0
+
+
 @pytest.mark.parametrize("az,alt", [(225.0, 25.0), (0.0, 90.0), (90.0, 1.0), (315.0, 60.0)])
 def test_hillshade_closed_form_equals_the_trig_chain(az, alt):
     """HillshadeOp (surface_ops.cuh) evaluates hillshade.py:20-35 -- np.gradient, atan, atan2, sin, cos --

@@ -55,9 +55,6 @@ def _declare(lib):
         "xrs_gci_f32": [P, P, P, I64, P],
         "xrs_sipi_f32": [P, P, P, P, I64, P],
         "xrs_ebbi_f32": [P, P, P, P, I64, P],
-        "xrs_zonal_init": [P, P, P, P, P, I, P],
-        "xrs_zonal_partials": [P, I, P, I, I64, P, I, P, I, D, P, P, P, P, P, P],
-        "xrs_zonal_partials_ex": [P, I, P, I, I64, P, I, P, I, D, I, I64, I64, P, P, P, P, P, P],
         "xrs_zonal_hash_init": [P, P, P, P, P, P, I, P, P],
         "xrs_zonal_hash_accumulate": [P, I, P, I, I64, I64, D, I, D, P, P, P, P, P, P, I, P, P],
         "xrs_zonal_hash_run": [P, I, P, I, I64, I64, I, D, I, D, P, P, P, P, P, P, I, P, I, P, P],

@@ -660,7 +660,10 @@ int xrs_conv3_strip(const float *in, int64_t in_pitch, float *out, int64_t out_p
                     const double *kernel, cudaStream_t s);  // surface.cu
 namespace xrs {
 bool try_box_stream(const float *in, int64_t in_pitch, float *out, int64_t out_pitch, int64_t H, int64_t W,
-                    const double *kernel, int kh, int kw, cudaStream_t s, int *rc);  // box_stream.cu
+                    const double *kernel, int kh, int kw, cudaStream_t s, int *rc);
+// box_stream.cu, NaN-skipping mode: focal.apply mean over an all-ones window
+bool try_box_nanmean(const float *in, int64_t in_pitch, float *out, int64_t out_pitch, int64_t H, int64_t W,
+                     int kh, int kw, cudaStream_t s, int *rc);  // box_stream.cu
 }
 
 extern "C" {
@@ -748,7 +751,15 @@ int xrs_focal_stat_f32(const float *in, int64_t in_pitch, float *out, int64_t ou
     if (rc) return rc;
     XRS_REQUIRE(stat >= XRS_STAT_MEAN && stat <= XRS_STAT_VAR, "unknown focal statistic");
     static thread_local MaskBits mask;
-    for (int i = 0; i < kh * kw; ++i) mask.m[i] = (kernel[i] == 1.0) ? 1 : 0;  // focal.py:323
+    bool all_ones = true;
+    for (int i = 0; i < kh * kw; ++i) {
+        mask.m[i] = (kernel[i] == 1.0) ? 1 : 0;  // focal.py:323
+        all_ones = all_ones && mask.m[i];
+    }
+    if (stat == XRS_STAT_MEAN && all_ones) {   // np.ones((k, k)): the running box, O(1) per cell
+        int brc = XRS_OK;
+        if (try_box_nanmean(in, in_pitch, out, out_pitch, H, W, kh, kw, (cudaStream_t)s, &brc)) return brc;
+    }
     TileGeom g;
     CUtensorMap tmap;
     const int sms = sm_count();

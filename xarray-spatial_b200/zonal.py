@@ -367,48 +367,6 @@ def allreduce_tables(ids, part, dev, comm):
     return union.astype(np.asarray(ids).dtype), {k: v.cpu().numpy() for k, v in dense.items()}
 
 
-def zonal_partials(zones_t, values_t, ids, nodata_values=None, pivot=None, comm=None):
-    """Run the kernel; returns dict of numpy arrays (count int64; s1, s2, min, max float64) and
-    the pivot used.  ids: sorted numpy array of candidate zone ids."""
-    import torch
-    dev = values_t.device
-    nz = len(ids)
-    ids_t = torch.as_tensor(np.asarray(ids, dtype=np.float64), device=dev)
-    if pivot is None:
-        pivot = np.full(nz, _sample_pivot(values_t, comm), dtype=np.float64)
-    piv_t = torch.as_tensor(np.asarray(pivot, dtype=np.float64), device=dev)
-    count = torch.empty(nz, dtype=torch.int64, device=dev)
-    s1 = torch.empty(nz, dtype=torch.float64, device=dev)
-    s2 = torch.empty(nz, dtype=torch.float64, device=dev)
-    vmin = torch.empty(nz, dtype=torch.float64, device=dev)
-    vmax = torch.empty(nz, dtype=torch.float64, device=dev)
-    P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
-    use_lut, lut_base = 0, 0
-    if nz and not zones_t.dtype.is_floating_point:
-        lo, hi = int(ids[0]), int(ids[-1])
-        if hi - lo < 8192 and nz <= 2048:
-            use_lut, lut_base = 1, lo
-    with torch.cuda.device(dev):
-        st = stream_ptr(values_t)
-        if nz:
-            _lib.call("xrs_zonal_init", P(count), P(s1), P(s2), P(vmin), P(vmax), nz, st)
-            _lib.call("xrs_zonal_partials_ex", P(values_t), _dtype_code(values_t), P(zones_t),
-                      _dtype_code(zones_t), values_t.numel(), P(ids_t), nz, P(piv_t),
-                      0 if nodata_values is None else 1,
-                      0.0 if nodata_values is None else float(nodata_values), use_lut, lut_base,
-                      int(values_t.shape[-1]) if values_t.dim() else 1,
-                      P(count), P(s1), P(s2), P(vmin), P(vmax), st)
-    if comm is not None and nz:
-        import torch.distributed as dist
-        dist.all_reduce(count, op=dist.ReduceOp.SUM, group=comm)
-        dist.all_reduce(s1, op=dist.ReduceOp.SUM, group=comm)
-        dist.all_reduce(s2, op=dist.ReduceOp.SUM, group=comm)
-        dist.all_reduce(vmin, op=dist.ReduceOp.MIN, group=comm)
-        dist.all_reduce(vmax, op=dist.ReduceOp.MAX, group=comm)
-    return dict(count=count.cpu().numpy(), s1=s1.cpu().numpy(), s2=s2.cpu().numpy(),
-                min=vmin.cpu().numpy(), max=vmax.cpu().numpy()), np.asarray(pivot, dtype=np.float64)
-
-
 def finalize(part, pivot, stats_funcs):
     """dict stat -> float64 column; zones without valid cells are NaN (zonal.py:153-162)."""
     cnt = part["count"].astype(np.float64)
