@@ -257,9 +257,24 @@ box_stream2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__rest
         const int64_t x = (int64_t)tile * S::kTileOutW - S::kPad + col;  // raster column of the lane's first cell
         const bool in_raster = x >= 0 && x < g.W;                          // W % 4 == 0: all four cells in or out
         const bool store_ok = emits && in_raster;
-        // MODE 0: out-of-raster columns may poison their own lane's sums (exactly the windows that contain
-        // them must be NaN).  MODE 1 skips them like any NaN cell, so they are masked and counted.
-        const bool watch = MODE == 1 || in_raster;
+        // Out-of-raster columns (NaN from the TMA unit) never vote a row "dirty".  MODE 0: they may poison
+        // their own lane's sums -- exactly the windows that contain them must be NaN.  MODE 1 skips them: the
+        // lane's cells are read as 0, and a window that reaches beyond the raster's left / right edge divides
+        // by the number of columns it really has (ncv) -- edge tiles stay on the fast path in both modes.
+        const bool watch = in_raster;
+        int ncv[4] = {kw, kw, kw, kw};
+        bool edge_warp = false;
+        if constexpr (MODE == 1) {
+            bool edge_lane = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t xc = x + j;
+                const int64_t lo = xc - RX < 0 ? 0 : xc - RX, hi = xc + RX > g.W - 1 ? g.W - 1 : xc + RX;
+                ncv[j] = (int)(hi - lo + 1);
+                edge_lane = edge_lane || (ncv[j] != kw);
+            }
+            edge_warp = __any_sync(0xffffffffu, edge_lane && in_raster);
+        }
         float *optr = out + y0 * out_pitch_elems + x;
 
         double V[4] = {0.0, 0.0, 0.0, 0.0};
@@ -279,6 +294,9 @@ box_stream2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__rest
                 for (int i = 0; i < kB2Rows; ++i) {
                     const float4 q = *reinterpret_cast<const float4 *>(se + i * S::kBoxW);
                     nv[i][0] = q.x; nv[i][1] = q.y; nv[i][2] = q.z; nv[i][3] = q.w;
+                    if constexpr (MODE == 1) {
+                        if (!in_raster) { nv[i][0] = 0.f; nv[i][1] = 0.f; nv[i][2] = 0.f; nv[i][3] = 0.f; }
+                    }
                 }
                 const float amax = bs_amax3(bs_amax3(bs_amax4(nv[0]), nv[1][0], nv[1][1]),
                                             bs_amax3(bs_amax4(nv[2]), nv[1][2], nv[1][3]), bs_amax4(nv[3]));
@@ -288,6 +306,9 @@ box_stream2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__rest
                     for (int i = 0; i < kB2Rows; ++i) {
                         const float4 q = *reinterpret_cast<const float4 *>(sl + i * S::kBoxW);
                         ov[i][0] = q.x; ov[i][1] = q.y; ov[i][2] = q.z; ov[i][3] = q.w;
+                        if constexpr (MODE == 1) {
+                            if (!in_raster) { ov[i][0] = 0.f; ov[i][1] = 0.f; ov[i][2] = 0.f; ov[i][3] = 0.f; }
+                        }
                     }
                     // column sums of output row i: V_i = V_{i-1} - old_{i-1} + new_i
                     double P[kB2Rows][4];
@@ -311,10 +332,14 @@ box_stream2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__rest
                                 __stcs(reinterpret_cast<float4 *>(optr),
                                        make_float4((float)fma(g.w, win[i][0], 0.0), (float)fma(g.w, win[i][1], 0.0),
                                                    (float)fma(g.w, win[i][2], 0.0), (float)fma(g.w, win[i][3], 0.0)));
-                            else
+                            else if (!edge_warp)
                                 __stcs(reinterpret_cast<float4 *>(optr),
                                        make_float4((float)bs_div_n(win[i][0], g.n_cells, g.w), (float)bs_div_n(win[i][1], g.n_cells, g.w),
                                                    (float)bs_div_n(win[i][2], g.n_cells, g.w), (float)bs_div_n(win[i][3], g.n_cells, g.w)));
+                            else
+                                __stcs(reinterpret_cast<float4 *>(optr),
+                                       make_float4((float)(win[i][0] / (double)(kh * ncv[0])), (float)(win[i][1] / (double)(kh * ncv[1])),
+                                                   (float)(win[i][2] / (double)(kh * ncv[2])), (float)(win[i][3] / (double)(kh * ncv[3]))));
                         }
                         optr += out_pitch_elems;
                     }
@@ -329,7 +354,8 @@ box_stream2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__rest
                     const int e = e0 + i;
                     if (e >= n_in) break;
                     const float4 q = *reinterpret_cast<const float4 *>(se + i * S::kBoxW);
-                    const float v[4] = {q.x, q.y, q.z, q.w};
+                    const bool zero_lane = MODE == 1 && !in_raster;
+                    const float v[4] = {zero_lane ? 0.f : q.x, zero_lane ? 0.f : q.y, zero_lane ? 0.f : q.z, zero_lane ? 0.f : q.w};
                     const bool row_dirty = __any_sync(0xffffffffu, watch && !(bs_amax4(v) < kBsHuge));
                     dirty = (dirty << 1) | (row_dirty ? 1u : 0u);
                     if (!row_dirty) {
@@ -354,7 +380,7 @@ box_stream2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__rest
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         res[j] = MODE == 0 ? (float)fma(g.w, w1[0][j], 0.0)    // + 0.0: an all-zero window is +0 like the reference's
-                                           : (float)bs_div_n(w1[0][j], g.n_cells, g.w);
+                                 : (edge_warp ? (float)(w1[0][j] / (double)(kh * ncv[j])) : (float)bs_div_n(w1[0][j], g.n_cells, g.w));
                     if (win_dirty) {   // warp-uniform
                         unsigned C1[1][4] = {{C[0], C[1], C[2], C[3]}}, wc[1][4];
                         bs_lanesum<RX, 1, unsigned>(C1, wc);
@@ -370,7 +396,7 @@ box_stream2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__rest
                                 if (wc[0][j] >> 16) {          // infinite / huge cells take part: the reference's order
                                     if (store_ok) res[j] = bs_direct_nanmean(in, in_pitch_elems, g.H, g.W, y, x + j, kh, kw);
                                 } else if (wc[0][j] & 0xffffu) {
-                                    res[j] = (float)(w1[0][j] / (g.n_cells - (double)(wc[0][j] & 0xffffu)));   // all skipped: 0 / 0 = NaN
+                                    res[j] = (float)(w1[0][j] / (double)(kh * ncv[j] - (int)(wc[0][j] & 0xffffu)));   // all skipped: 0 / 0 = NaN
                                 }
                             }
                         }
@@ -380,7 +406,7 @@ box_stream2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__rest
 
                     // retire input row e - (kh - 1), the oldest row of the window
                     const float4 qo = *reinterpret_cast<const float4 *>(sl + i * S::kBoxW);
-                    const float vo[4] = {qo.x, qo.y, qo.z, qo.w};
+                    const float vo[4] = {zero_lane ? 0.f : qo.x, zero_lane ? 0.f : qo.y, zero_lane ? 0.f : qo.z, zero_lane ? 0.f : qo.w};
                     const bool old_dirty = (dirty >> (kh - 1)) & 1u;
                     if (!old_dirty) {
 #pragma unroll
