@@ -122,7 +122,9 @@ int xrs_convolve2d_f32(const float *in, int64_t in_pitch, float *out, int64_t ou
                        xrs_stream_t s);
 /* focal._focal_stats_cupy (focal.py:757-779) with the CPU semantics of `_apply_numpy`
  * (focal.py:305-326) + reducers (:268-302): cells where kernel == 1 participate, NaN and
- * out-of-raster cells are skipped.  `stat` is an xrs_focal_stat. */
+ * out-of-raster cells are skipped.  `stat` is an xrs_focal_stat.  XRS_STAT_MEAN over a kernel of all
+ * ones (np.ones((kh, kw)), the reference's FocalApply benchmark; odd kh, kw <= 25) runs on the running-box
+ * kernel in NaN-skipping mode, O(1) work per cell; everything else on the tiled kernels. */
 int xrs_focal_stat_f32(const float *in, int64_t in_pitch, float *out, int64_t out_pitch,
                        int64_t H, int64_t W, const double *kernel, int kh, int kw, int stat,
                        xrs_stream_t s);
@@ -263,10 +265,16 @@ int xrs_host_alloc(void **ptr, int64_t bytes);
 int xrs_host_free(void *ptr);
 
 /* test / profiling hooks: which kernel the last launch on this thread chose -- 0 cp.async strip
- * kernel, 1 TMA strip kernel, 2 direct-ingest TMA kernel, 3 summed-area box convolve, 4 generic
- * tiled convolve, 5 bounds-checked convolve fallback, 6 fused focal statistics -- and with how many CTAs */
+ * kernel, 1 TMA strip kernel, 2 direct-ingest TMA kernel, 3 running-box kernel (uniform convolve_2d, focal.apply
+ * mean over an all-ones window), 4 generic tiled convolve, 5 bounds-checked convolve fallback, 6 fused focal
+ * statistics -- and with how many CTAs */
 int xrs_debug_last_used_tma(void);
 int xrs_debug_last_grid(void);
+/* host-only test hook: the row-segment height the persistent kernels pick for a raster of H rows cut into
+ * n_tiles column tiles, dealt round-robin to `resident` CTAs (at least min_rows, rows + lead a multiple of
+ * quantum, about `want` tasks per CTA): minimises ceil(tasks / resident) x (rows + lead). */
+int64_t xrs_debug_pick_seg_rows(int64_t H, int64_t n_tiles, int64_t resident, int64_t min_rows, int64_t lead,
+                                int64_t quantum, int64_t want);
 
 /* ------------------------------------------------------------------ synthetic inputs
  * Deterministic fBm-like terrain (value-noise octaves), a pure function of

@@ -340,3 +340,42 @@ def test_zonal_stats_argument_checks_without_a_gpu():
         zonal.stats(z, v, stats_funcs="mean")
     with pytest.raises(ValueError, match="equal shapes"):
         zonal.stats(xb.DataArray(np.zeros((2, 3), np.int32), dims=("y", "x")), v)
+
+
+def test_row_segments_are_wave_balanced():
+    """pick_seg_rows (stencil3.cuh, through the host-only hook xrs_debug_pick_seg_rows): tasks = tiles x segments
+    are dealt round-robin to the resident CTAs, so a kernel lasts ceil(tasks / resident) task-times.  The chosen
+    segment height must (a) respect the minimum height and the chunk quantum, (b) never be worse than the
+    round-1 rule (round the segment count UP to ~8 tasks per CTA), and (c) stay within 4 % of the ideal
+    H * tiles / resident rows per CTA on the benchmark shapes -- the round-1 rule ran the fused suite in 9
+    waves instead of 8.03 (1188 tasks on 1184 slots)."""
+    import xrspatial_b200
+    lib = xrspatial_b200._lib.lib()
+
+    def cost(H, n_tiles, resident, rows, lead):
+        segs = -(-H // rows)
+        return -(-(segs * n_tiles) // resident) * (rows + lead)
+
+    def round1_rows(H, n_tiles, resident, quantum):
+        want = -(-(resident * 8) // n_tiles)
+        rows = max(32, -(-H // want))
+        rows = min(rows, H)
+        return max(1, -(-(rows + 2) // quantum) * quantum - 2)
+
+    cases = [(32768, 32, 296, 4), (32768, 16, 148, 2), (32768, 22, 148, 8), (65536, 64, 296, 4), (8192, 64, 296, 4),
+             (10000, 15, 148, 2), (30000, 30, 296, 4), (2048, 2, 296, 4), (100, 1, 296, 4), (3, 1, 296, 4),
+             (4321, 7, 148, 8), (16384, 40, 296, 4)]
+    for H, n_tiles, resident, quantum in cases:
+        rows = lib.xrs_debug_pick_seg_rows(H, n_tiles, resident, 32, 2, quantum, 8)
+        assert rows >= 1 and (rows + 2) % quantum == 0, (H, n_tiles, rows)
+        assert rows >= min(32, H) - quantum, (H, n_tiles, rows)
+        new, old = cost(H, n_tiles, resident, rows, 2), cost(H, n_tiles, resident, round1_rows(H, n_tiles, resident, quantum), 2)
+        assert new <= old, (H, n_tiles, resident, rows, new, old)
+        ideal = H * n_tiles / resident
+        if H * n_tiles >= 64 * resident * 32:          # enough rows for every CTA to get several tasks
+            assert new <= 1.04 * ideal + 40, (H, n_tiles, resident, rows, new, ideal)
+    # the running box: lead-in rows kh - 1, batches of 4, tall segments
+    for kh, n_tiles in ((9, 40), (25, 46), (5, 40)):
+        rows = lib.xrs_debug_pick_seg_rows(32768, n_tiles, 296, 12 * kh, kh - 1, 4, 4)
+        assert (rows + kh - 1) % 4 == 0 and rows >= 12 * kh
+        assert cost(32768, n_tiles, 296, rows, kh - 1) <= 1.06 * 32768 * n_tiles / 296

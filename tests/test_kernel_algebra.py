@@ -341,3 +341,72 @@ def test_order_preserving_float_keys_of_the_zonal_table():
     order = np.argsort(key, kind="stable")
     assert (np.diff(f[order].astype(np.float64)) >= 0).all()
     assert key[f == np.inf][0] == np.int32(0x7f800000) and (key[np.isfinite(f)] < np.int32(0x7f800000)).all()
+
+
+def _pair_counts_two_runs(zones, values, nodata=None):
+    """NumPy statement of zonal_pair_kernel's bookkeeping (zonal_hash.cu): a lane walks down its 4 columns and
+    keeps TWO open runs (zone, value, count); a cell whose pair is one of them just counts, a third pair evicts
+    the run used less recently into the table.  A 4-row batch is "clean" when every cell lies in the zone of
+    the run used last and holds one of the two values whose runs are in that zone -- then the batch is counted
+    by value compares alone (an invalid cell matches neither value, so validity needs no test there)."""
+    H, W = zones.shape
+    table = {}
+
+    def merge(z, v, c):
+        if c:
+            table[(int(z), float(v))] = table.get((int(z), float(v)), 0) + int(c)
+
+    for x0 in range(0, W, 4):
+        z0 = z1 = 0
+        v0 = v1 = np.float32(np.nan)
+        c0 = c1 = 0
+        last1 = False
+        for y0 in range(0, H, 4):
+            zb, vb = zones[y0:y0 + 4, x0:x0 + 4], values[y0:y0 + 4, x0:x0 + 4]
+            zc = z1 if last1 else z0
+            m0 = int((vb == v0).sum()) if z0 == zc else 0
+            m1 = int((vb == v1).sum()) if z1 == zc else 0
+            if zb.shape == (4, 4) and (zb == zc).all() and m0 + m1 == 16:
+                c0, c1 = c0 + m0, c1 + m1
+                last1 = bool(z1 == zc and vb[3, 3] == v1)
+                continue
+            for zk, fr in zip(zb.ravel(), vb.ravel()):        # row-major inside the batch, like the kernel
+                f = np.float32(fr + np.float32(0.0))
+                if not np.isfinite(f) or (nodata is not None and f == nodata):
+                    continue
+                if zk == z0 and f == v0:
+                    c0, last1 = c0 + 1, False
+                elif zk == z1 and f == v1:
+                    c1, last1 = c1 + 1, True
+                elif last1:
+                    merge(z0, v0, c0)
+                    z0, v0, c0, last1 = zk, f, 1, False
+                else:
+                    merge(z1, v1, c1)
+                    z1, v1, c1, last1 = zk, f, 1, True
+        merge(z0, v0, c0)
+        merge(z1, v1, c1)
+    return table
+
+
+def test_two_open_runs_count_every_pair_exactly_once():
+    """The pair histogram behind `majority` / `crosstab`: whatever the flip-flop pattern between classes, zone
+    boundaries, NaN / inf / nodata cells and -0.0, the two-run bookkeeping counts every valid (zone, value)
+    pair exactly once (compared with a direct histogram)."""
+    rng = np.random.default_rng(2)
+    H, W = 64, 24
+    for trial in range(6):
+        base = np.cumsum(rng.standard_normal((H, W)) * 0.7, axis=0)          # smooth down the columns: long runs
+        values = np.floor(base + rng.standard_normal((H, W)) * (0.2 + 0.2 * trial)).astype(np.float32)   # + flip-flops
+        zones = (np.arange(H)[:, None] // (8 + trial) * 3 + np.arange(W)[None, :] // 5).astype(np.int32)
+        values[rng.random((H, W)) < 0.03] = np.nan
+        values[5, 7] = np.inf
+        values[9, 3] = np.float32(-0.0)
+        nodata = np.float32(2.0) if trial % 2 else None
+        got = _pair_counts_two_runs(zones, values, nodata)
+        ok = np.isfinite(values) & ((values != nodata) if nodata is not None else True)
+        ref = {}
+        for z, v in zip(zones[ok], values[ok]):
+            k = (int(z), float(v + np.float32(0.0)))
+            ref[k] = ref.get(k, 0) + 1
+        assert got == ref

@@ -71,6 +71,7 @@ def _declare(lib):
                                   ctypes.c_float, P],
         "xrs_debug_last_used_tma": [],
         "xrs_debug_last_grid": [],
+        "xrs_debug_pick_seg_rows": [I64, I64, I64, I64, I64, I64, I64],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -78,6 +79,7 @@ def _declare(lib):
         fn.restype = I
     lib.xrs_last_error_string.argtypes = []
     lib.xrs_last_error_string.restype = ctypes.c_char_p
+    lib.xrs_debug_pick_seg_rows.restype = I64
     return sig
 
 

@@ -132,5 +132,10 @@ int xrs_host_free(void *ptr) {
 // test hook: which kernel the last launch on this thread chose (codes in xrs_b200.h)
 int xrs_debug_last_used_tma(void) { return xrs::last_launch_info().used_tma; }
 int xrs_debug_last_grid(void) { return xrs::last_launch_info().grid; }
+// test hook (host only, no device needed): the row-segment height the persistent kernels would pick
+int64_t xrs_debug_pick_seg_rows(int64_t H, int64_t n_tiles, int64_t resident, int64_t min_rows, int64_t lead,
+                                int64_t quantum, int64_t want) {
+    return xrs::pick_seg_rows(H, n_tiles, resident, min_rows, lead, quantum, want);
+}
 
 }  // extern "C"
