@@ -569,6 +569,55 @@ def test_full_size_properties(xb, side):
     assert bool(torch.equal(torch.nan_to_num(whole[a0:b0], nan=-5.0), torch.nan_to_num(part, nan=-5.0)))
 
 
+def test_full_size_box_and_zonal_properties(xb):
+    """The running box (convolve_2d with uniform taps, focal.apply mean over all-ones windows) and the zonal
+    group-by at the benchmark size 32768^2, through properties that need no oracle: the mean of a plane over a
+    symmetric window is the plane's value at the window's centre; a constant stays a constant under clamped
+    NaN-skipping windows; block zones of a plane have closed-form counts, means, minima and maxima."""
+    from xrspatial_b200 import focal
+    from xrspatial_b200.convolution import convolve_2d
+    side = 32768
+    free, _ = torch.cuda.mem_get_info()
+    if free < side * side * 4 * 5:
+        pytest.skip("not enough device memory for a %d^2 raster" % side)
+    ys = torch.arange(side, device="cuda", dtype=torch.float32)[:, None]
+    xs = torch.arange(side, device="cuda", dtype=torch.float32)[None, :]
+    ramp = (0.5 * xs + 0.25 * ys).contiguous()          # exact in float32, < 2^15
+    for k in (9, 25):
+        r = k // 2
+        out = convolve_2d(ramp, np.ones((k, k)) / (k * k))
+        assert used_tma(xb) == 3
+        inner = out[r:-r, r:-r]
+        assert float((inner - ramp[r:-r, r:-r]).abs().max()) <= 1e-5 * 24576.0     # the window's centre value
+        assert bool(torch.isnan(out[:r]).all() and torch.isnan(out[-r:]).all() and torch.isnan(out[:, :r]).all()
+                    and torch.isnan(out[:, -r:]).all())                              # the reference's NaN ring
+        assert not bool(torch.isnan(inner).any())
+        del out, inner
+    m = focal.apply(da(xb, ramp), np.ones((5, 5))).data
+    assert used_tma(xb) == 3
+    assert float((m[2:-2, 2:-2] - ramp[2:-2, 2:-2]).abs().max()) <= 1e-5 * 24576.0
+    # clamped corner window: rows 0..2 x columns 0..2 of the plane -> its value at (1, 1)
+    assert abs(float(m[0, 0]) - 0.75) <= 1e-6 and not bool(torch.isnan(m).any())
+    del m
+    # block zones of the plane: 32 x 32 blocks of 1024 x 1024 cells
+    zones = ((ys.to(torch.int32) // 1024) * 32 + (xs.to(torch.int32) // 1024)).contiguous()
+    df = xb.zonal_stats(da(xb, zones), da(xb, ramp), stats_funcs=["mean", "max", "min", "count", "sum"])
+    zid = np.asarray(df["zone"])
+    assert np.array_equal(zid, np.arange(1024))
+    by, bx = zid // 32, zid % 32
+    assert np.array_equal(np.asarray(df["count"]), np.full(1024, 1024.0 * 1024.0))
+    lo = 0.5 * (bx * 1024) + 0.25 * (by * 1024)
+    hi = 0.5 * (bx * 1024 + 1023) + 0.25 * (by * 1024 + 1023)
+    assert np.array_equal(np.asarray(df["min"]), lo) and np.array_equal(np.asarray(df["max"]), hi)
+    np.testing.assert_allclose(np.asarray(df["mean"]), 0.5 * (lo + hi), rtol=1e-12)       # exact sums of a plane
+    np.testing.assert_allclose(np.asarray(df["sum"]), 0.5 * (lo + hi) * 1024.0 * 1024.0, rtol=1e-12)
+    # a categorical raster with a known majority: class = block row parity, except a minority stripe
+    ramp.copy_(((ys.to(torch.int32) // 1024) % 2).to(torch.float32).expand(side, side))
+    ramp[:, ::7] = 5.0
+    df = xb.zonal_stats(da(xb, zones), da(xb, ramp), stats_funcs=["majority"])
+    assert np.array_equal(np.asarray(df["majority"]), (by % 2).astype(np.float64))
+
+
 def test_hotspots_vs_reference_outputs(xb, refout):
     r = refout
     agg = da(xb, dev(r["hotspots.dem"]))
