@@ -25,8 +25,8 @@
 //   * 7 consumer warps + 1 producer warp = 256 threads: 128 registers per thread at two CTAs per SM (no
 //     spills in the fast path; 8 + 1 warps are capped at 96 registers: 0.79 instead of 0.87 at k = 9);
 //   * row segments are chosen so that no CTA runs one task more than the others (pick_seg_rows).
-// B200, 32768^2 (profiles/r02s2_*.txt): k = 5 / 9 / 15 / 25: 751 / 714 / 685 / 559 Gcells/s = 0.92 / 0.87 /
-// 0.84 / 0.68 of the measured HBM copy peak, outputs bit-identical to the first generation.
+// B200, 32768^2 (profiles/r02s2_*.txt, bench_r02s2_n1.json): k = 5 / 9 / 15 / 25: 751 / 717 / 685 / 570 Gcells/s =
+// 0.92 / 0.87 / 0.84 / 0.69 of the measured HBM copy peak, outputs bit-identical to the first generation.
 // Numerics.  The reference accumulates fma(w, v, acc) tap by tap in float64; here the window sum is
 // formed in float64 (sums of float32 cells: rounding ~1e-16 of the window's magnitude) and scaled
 // once -- far inside the 1e-5 bar of the float32 result.  Running sums are only trustworthy while
