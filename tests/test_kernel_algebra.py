@@ -343,6 +343,78 @@ def test_order_preserving_float_keys_of_the_zonal_table():
     assert key[f == np.inf][0] == np.int32(0x7f800000) and (key[np.isfinite(f)] < np.int32(0x7f800000)).all()
 
 
+def _lane_sum_windows_wide(v, rx):
+    """NumPy statement of bw_lanesum / bw_cell of the WIDE variant of the running box (a tuning note, not built:
+    scripts/tune/box_stream_wide_variant.cu.txt -- measured slower than the shipped kernel): 8 columns per lane, 256 per warp,
+    radius <= 12.  Same algebra as _lane_sum_windows: suffix of the lane the window starts in + prefix of the
+    lane it ends in + the totals of whole lanes in between; a window inside one lane is summed directly."""
+    q, m = divmod(rx, 8)
+    lanes = np.arange(32)
+
+    def frm(x, d):
+        src = lanes + d
+        src = np.where((src < 0) | (src > 31), lanes, src)
+        return x[src]
+
+    pre = np.cumsum(v, axis=1)
+    suf = np.empty_like(v)
+    suf[:, 7] = v[:, 7]
+    for j in range(6, 0, -1):
+        suf[:, j] = v[:, j] + suf[:, j + 1]
+    suf[:, 0] = pre[:, 7]
+    tot = pre[:, 7]
+    tl, tr = (frm(tot, -1), frm(tot, 1)) if (q == 1 and m > 0) else (np.zeros(32), np.zeros(32))
+    win = np.empty_like(v)
+    for j in range(8):
+        a, b = j - m, j + m
+        if q == 0 and a >= 0 and b <= 7:
+            if a == 0:
+                win[:, j] = pre[:, b]
+            elif b == 7:
+                win[:, j] = suf[:, a]
+            else:
+                acc = v[:, a].copy()
+                for c in range(a + 1, b + 1):
+                    acc = acc + v[:, c]
+                win[:, j] = acc
+            continue
+        dl, ia = -q - (1 if a < 0 else 0), (a + 8) & 7
+        dh, ib = q + (1 if b >= 8 else 0), b & 7
+        ends = frm(suf[:, ia], dl) + frm(pre[:, ib], dh)
+        if q == 0:
+            win[:, j] = ends + tot if (a < 0 and b >= 8) else ends
+        else:
+            full = tot
+            if a < 0:
+                full = full + tl
+            if b >= 8:
+                full = full + tr
+            win[:, j] = ends + full
+    return win
+
+
+@pytest.mark.parametrize("rx", range(1, 13))
+def test_wide_lane_sum_windows_equal_direct_window_sums(rx):
+    """The wide variant's shuffle algebra (8 columns per lane): every column whose float4 half emits (half start
+    in [pad, 256 - pad), pad = rx rounded up to a multiple of 4) gets the direct sum of its 2 rx + 1 columns, and
+    NaN columns beyond the raster's edge -- whole lanes, or ONE half of a lane -- reach exactly the windows that
+    contain them."""
+    rng = np.random.default_rng(100 + rx)
+    cols = rng.integers(-1000, 1000, 256).astype(np.float64)
+    pad = (rx + 3) // 4 * 4
+    x = np.arange(pad, 256 - pad)
+    for nan_cols in ((), range(0, pad), range(256 - pad, 256), range(0, 4), range(0, 12), range(252, 256), (pad + rx,)):
+        c = cols.copy()
+        c[list(nan_cols)] = np.nan
+        with np.errstate(invalid="ignore"):
+            win = _lane_sum_windows_wide(c.reshape(32, 8), rx).reshape(256)
+        direct = np.array([c[i - rx:i + rx + 1].sum() for i in x])
+        np.testing.assert_array_equal(win[x], direct)
+    cnt = rng.integers(0, 3, 256).astype(np.float64)
+    win = _lane_sum_windows_wide(cnt.reshape(32, 8), rx).reshape(256)
+    np.testing.assert_array_equal(win[x], np.array([cnt[i - rx:i + rx + 1].sum() for i in x]))
+
+
 def _pair_counts_two_runs(zones, values, nodata=None):
     """NumPy statement of zonal_pair_kernel's bookkeeping (zonal_hash.cu): a lane walks down its 4 columns and
     keeps TWO open runs (zone, value, count); a cell whose pair is one of them just counts, a third pair evicts
