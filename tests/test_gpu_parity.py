@@ -569,46 +569,6 @@ def test_full_size_properties(xb, side):
     assert bool(torch.equal(torch.nan_to_num(whole[a0:b0], nan=-5.0), torch.nan_to_num(part, nan=-5.0)))
 
 
-def test_running_box_every_radius(xb):
-    """The running box at every window width 5..25 (every compile-time radius: each has its own shuffle
-    pattern), square and 3-row windows, against the oracle: clean raster, then NaN / inf / sentinel cells
-    including ones next to the raster's edges (a window that holds an infinite cell AND reaches beyond the raster
-    is NaN, not the tap-order recompute).  The same loop run on the CPU through the NumPy statement of the
-    algorithm (tests/test_kernel_algebra.py `_box_running`) meets these expectations at every width."""
-    from xrspatial_b200 import focal
-    from xrspatial_b200.convolution import convolve_2d
-    rng = np.random.default_rng(4242)
-    z = terrain(rng, 150, 2052)
-    d = z.copy()
-    d[rng.random(d.shape) < 0.001] = np.nan
-    d[40, 2] = np.inf                    # within every radius >= 2 of the left edge
-    d[90, 2049] = np.float32(3.4028235e38)
-    d[100, 1000] = -np.inf
-    d[3, 500] = np.inf                   # near the top edge
-    for kw in range(5, 26, 2):
-        for kh in sorted({kw, 3}):
-            kern = np.full((kh, kw), 1.0 / (kh * kw))
-            for data in (z, d):
-                ref = o.convolve_2d(data, kern, nthreads=16)
-                got = convolve_2d(dev(data), kern).cpu().numpy()
-                assert used_tma(xb) == 3
-                np.testing.assert_array_equal(np.isnan(got), np.isnan(ref), err_msg="NaN mask %dx%d" % (kh, kw))
-                fin = np.isfinite(ref) & (np.abs(ref) < 1e20)
-                assert_close_f32(np.where(fin, got, 0), np.where(fin, ref, 0), atol=1e-6 * 4000.0, what="box %dx%d" % (kh, kw))
-                odd = ~np.isnan(ref) & ~fin
-                np.testing.assert_allclose(got[odd], ref[odd], rtol=1e-6)
-        if kw in (7, 11, 17, 19, 21, 23):
-            kern = np.ones((kw, kw))
-            ref = o.focal_apply(d, kern, "mean", nthreads=16)
-            got = host(focal.apply(da(xb, dev(d)), kern))
-            assert used_tma(xb) == 3
-            np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
-            fin = np.isfinite(ref) & (np.abs(ref) < 1e20)
-            assert_close_f32(np.where(fin, got, 0), np.where(fin, ref, 0), what="apply mean %dx%d" % (kw, kw))
-            odd = ~np.isnan(ref) & ~fin
-            np.testing.assert_allclose(got[odd], ref[odd], rtol=1e-6)
-
-
 def test_full_size_box_and_zonal_properties(xb):
     """The running box (convolve_2d with uniform taps, focal.apply mean over all-ones windows) and the zonal
     group-by at the benchmark size 32768^2, through properties that need no oracle: the mean of a plane over a
@@ -1170,3 +1130,43 @@ def test_crosstab_3d(xb, known, refout):
         assert list(df.columns) == ["zone", 2001.0, 2003.0, 2004.0]
         np.testing.assert_allclose(np.asarray(df.values, dtype=np.float64), r["crosstab3d." + agg], rtol=1e-5, atol=1e-4,
                                    err_msg=agg)
+
+
+def test_running_box_every_radius(xb):
+    """The running box at every window width 5..25 (every compile-time radius: each has its own shuffle
+    pattern), square and 3-row windows, against the oracle: clean raster, then NaN / inf / sentinel cells
+    including ones next to the raster's edges (a window that holds an infinite cell AND reaches beyond the raster
+    is NaN, not the tap-order recompute).  The same loop run on the CPU through the NumPy statement of the
+    algorithm (tests/test_kernel_algebra.py `_box_running`) meets these expectations at every width."""
+    from xrspatial_b200 import focal
+    from xrspatial_b200.convolution import convolve_2d
+    rng = np.random.default_rng(4242)
+    z = terrain(rng, 150, 2052)
+    d = z.copy()
+    d[rng.random(d.shape) < 0.001] = np.nan
+    d[40, 2] = np.inf                    # within every radius >= 2 of the left edge
+    d[90, 2049] = np.float32(3.4028235e38)
+    d[100, 1000] = -np.inf
+    d[3, 500] = np.inf                   # near the top edge
+    for kw in range(5, 26, 2):
+        for kh in sorted({kw, 3}):
+            kern = np.full((kh, kw), 1.0 / (kh * kw))
+            for data in (z, d):
+                ref = o.convolve_2d(data, kern, nthreads=16)
+                got = convolve_2d(dev(data), kern).cpu().numpy()
+                assert used_tma(xb) == 3
+                np.testing.assert_array_equal(np.isnan(got), np.isnan(ref), err_msg="NaN mask %dx%d" % (kh, kw))
+                fin = np.isfinite(ref) & (np.abs(ref) < 1e20)
+                assert_close_f32(np.where(fin, got, 0), np.where(fin, ref, 0), atol=1e-6 * 4000.0, what="box %dx%d" % (kh, kw))
+                odd = ~np.isnan(ref) & ~fin
+                np.testing.assert_allclose(got[odd], ref[odd], rtol=1e-6)
+        if kw in (7, 11, 17, 19, 21, 23):
+            kern = np.ones((kw, kw))
+            ref = o.focal_apply(d, kern, "mean", nthreads=16)
+            got = host(focal.apply(da(xb, dev(d)), kern))
+            assert used_tma(xb) == 3
+            np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
+            fin = np.isfinite(ref) & (np.abs(ref) < 1e20)
+            assert_close_f32(np.where(fin, got, 0), np.where(fin, ref, 0), what="apply mean %dx%d" % (kw, kw))
+            odd = ~np.isnan(ref) & ~fin
+            np.testing.assert_allclose(got[odd], ref[odd], rtol=1e-6)

@@ -343,6 +343,77 @@ def test_order_preserving_float_keys_of_the_zonal_table():
     assert key[f == np.inf][0] == np.int32(0x7f800000) and (key[np.isfinite(f)] < np.int32(0x7f800000)).all()
 
 
+def _compile_lane_sum_templates(tmp_path):
+    """The device templates bs_from / bs_cell / bs_lanesum, cut out of box_stream.cu verbatim and compiled for the
+    HOST with a 32-lane value type whose shuffles have the hardware's semantics (a lane past the warp's end
+    reads itself): every compile-time radius is instantiated from the shipped source, not from a restatement."""
+    import ctypes
+    import subprocess
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "xarray-spatial_b200", "csrc",
+                            "box_stream.cu")).read()
+    a = src.index("// the value lane (l + D) holds")
+    b = src.index("__device__ __forceinline__ uint32_t bs_bits(int n)")
+    body = src[a:b]
+    host = r"""
+#include <cmath>
+#define __device__
+#define __forceinline__ inline
+struct Lanes {
+    double v[32];
+    Lanes() {}
+    Lanes(double x) { for (int i = 0; i < 32; ++i) v[i] = x; }
+};
+inline Lanes operator+(const Lanes &a, const Lanes &b) { Lanes r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] + b.v[i]; return r; }
+inline Lanes __shfl_down_sync(unsigned, const Lanes &x, int d) { Lanes r; for (int l = 0; l < 32; ++l) r.v[l] = l + d <= 31 ? x.v[l + d] : x.v[l]; return r; }
+inline Lanes __shfl_up_sync(unsigned, const Lanes &x, int d) { Lanes r; for (int l = 0; l < 32; ++l) r.v[l] = l - d >= 0 ? x.v[l - d] : x.v[l]; return r; }
+// names of the float64-only branch of bs_from (discarded for Lanes, but parsed)
+int __double2loint(double); int __double2hiint(double); double __hiloint2double(int, int);
+int __shfl_down_sync(unsigned, int, int); int __shfl_up_sync(unsigned, int, int);
+""" + body + r"""
+template <int RX> static void run1(const double *cols, double *out) {
+    Lanes v[1][4], w[1][4];
+    for (int l = 0; l < 32; ++l) for (int j = 0; j < 4; ++j) v[0][j].v[l] = cols[4 * l + j];
+    bs_lanesum<RX, 1, Lanes>(v, w);
+    for (int l = 0; l < 32; ++l) for (int j = 0; j < 4; ++j) out[4 * l + j] = w[0][j].v[l];
+}
+extern "C" int lane_sum(int rx, const double *cols, double *out) {
+    switch (rx) {
+        case 1: run1<1>(cols, out); break;   case 2: run1<2>(cols, out); break;   case 3: run1<3>(cols, out); break;
+        case 4: run1<4>(cols, out); break;   case 5: run1<5>(cols, out); break;   case 6: run1<6>(cols, out); break;
+        case 7: run1<7>(cols, out); break;   case 8: run1<8>(cols, out); break;   case 9: run1<9>(cols, out); break;
+        case 10: run1<10>(cols, out); break; case 11: run1<11>(cols, out); break; case 12: run1<12>(cols, out); break;
+        default: return 1;
+    }
+    return 0;
+}
+"""
+    cpp = os.path.join(str(tmp_path), "lane_sum_host.cpp")
+    so = os.path.join(str(tmp_path), "lane_sum_host.so")
+    open(cpp, "w").write(host)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-o", so, cpp])
+    lib = ctypes.CDLL(so)
+    lib.lane_sum.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    return lib
+
+
+def test_shipped_lane_sum_templates_on_the_host(tmp_path):
+    """Every radius 1..12 of the SHIPPED templates (compiled for the host, see above) against direct window sums,
+    with NaN columns beyond either edge of the strip: this is the code the GPU runs, minus the hardware."""
+    lib = _compile_lane_sum_templates(tmp_path)
+    rng = np.random.default_rng(77)
+    for rx in range(1, 13):
+        pad = (rx + 3) // 4 * 4
+        x = np.arange(pad, 128 - pad)
+        for nan_cols in ((), range(0, pad), range(128 - pad, 128), (pad + rx,)):
+            cols = rng.integers(-1000, 1000, 128).astype(np.float64)
+            cols[list(nan_cols)] = np.nan
+            out = np.empty(128)
+            assert lib.lane_sum(rx, cols.ctypes.data, out.ctypes.data) == 0
+            with np.errstate(invalid="ignore"):
+                direct = np.array([cols[i - rx:i + rx + 1].sum() for i in x])
+            np.testing.assert_array_equal(out[x], direct, err_msg="radius %d" % rx)
+
+
 def _lane_sum_windows_wide(v, rx):
     """NumPy statement of bw_lanesum / bw_cell of the WIDE variant of the running box (a tuning note, not built:
     scripts/tune/box_stream_wide_variant.cu.txt -- measured slower than the shipped kernel): 8 columns per lane, 256 per warp,
