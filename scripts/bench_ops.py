@@ -79,7 +79,7 @@ del d64, a64
 for k in (3, 9, 25):
     kern = np.ones((k, k)) / (k * k)
     add("convolve_2d k=%d uniform (ones/k^2)" % k, timeit(lambda: convolve_2d(dem, kern), n=max(3, reps // 2)), 8,
-        note="k=3: strip kernel; k>3: summed-area box path, HBM / shared-memory bound")
+        note="k=3: strip kernel; k>3: running-box kernel (box_stream.cu)")
 krng = np.random.default_rng(7)
 for k in (9, 25):
     kern = krng.standard_normal((k, k))

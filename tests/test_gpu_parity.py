@@ -223,8 +223,8 @@ def test_convolve_sizes_vs_oracle(xb, k):
 
 @pytest.mark.parametrize("kh,kw", [(5, 5), (9, 9), (25, 25), (3, 7), (7, 3), (1, 5), (25, 3)])
 def test_convolve_uniform_kernels_take_the_box_path(xb, kh, kw):
-    """All-equal taps (np.ones / k**2, the mean filter) go through the summed-area kernel; NaN / inf
-    cells poison the table and must come back through the tap-by-tap recompute."""
+    """All-equal taps (np.ones / k**2, the mean filter) go through the running-box kernel; NaN / inf cells are
+    kept out of the running sums: NaN windows are NaN, inf windows come back through the tap-by-tap recompute."""
     from xrspatial_b200.convolution import convolve_2d
     rng = np.random.default_rng(100 * kh + kw)
     z = terrain(rng, 150, 388)

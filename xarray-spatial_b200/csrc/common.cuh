@@ -15,7 +15,7 @@ void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
 
 struct LaunchInfo {  // for tests / profiling: what the last launch on this thread chose
-    int used_tma;    // 0 cp.async strip kernel, 1 TMA strip kernel, 2 direct-ingest, 3 summed-area box convolve,
+    int used_tma;    // 0 cp.async strip kernel, 1 TMA strip kernel, 2 direct-ingest, 3 running-box kernel,
                      // 4 generic tiled convolve, 5 bounds-checked fallback
     int grid, block, smem_bytes;
 };
