@@ -1,3 +1,5 @@
+# historical record of a GPU call of round 2, second session: `scripts/tune/box_sweep2.py` is the earlier version of
+# scripts/tune/box_zonal_sweep.py (it could still switch to the first-generation kernel and to 8 / 9 consumer warps).
 # second session of round 2, GPU call 1: parity of the new box / pair kernels, A/B sweep, ncu, bench line
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/s2_pytest.txt; tail -6 gpurun_out/s2_pytest.txt

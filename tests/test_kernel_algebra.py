@@ -553,3 +553,51 @@ def test_two_open_runs_count_every_pair_exactly_once():
             k = (int(z), float(v + np.float32(0.0)))
             ref[k] = ref.get(k, 0) + 1
         assert got == ref
+
+
+def test_shipped_division_and_float_keys_on_the_host(tmp_path):
+    """Two more device helpers cut out of the shipped sources and compiled for the host: bs_div_n (box_stream.cu;
+    the window sum divided by the window size) against the float64 division, and zh_fkey / zh_funkey
+    (zonal_hash.cu; order-preserving int32 keys of float32 values, so that min / max are native integer atomics)
+    against float ordering and a bit-exact round trip."""
+    import ctypes
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    box = open(os.path.join(root, "xarray-spatial_b200", "csrc", "box_stream.cu")).read()
+    zh = open(os.path.join(root, "xarray-spatial_b200", "csrc", "zonal_hash.cu")).read()
+    a = box.index("__device__ __forceinline__ double bs_div_n(")
+    div_src = box[a:box.index("}", box.index("return fma(", a)) + 1]
+    a = zh.index("__device__ __forceinline__ int zh_fkey(float f)")
+    key_src = zh[a:zh.index("template <typename VT> struct ZhMinMax")]
+    host = r"""
+#include <cmath>
+#include <cstring>
+#define __device__
+#define __forceinline__ inline
+static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+""" + div_src + "\n" + key_src + r"""
+extern "C" double div_n(double c, double n) { return bs_div_n(c, n, 1.0 / n); }
+extern "C" int fkey(float f) { return zh_fkey(f); }
+extern "C" float funkey(int k) { return zh_funkey(k); }
+"""
+    cpp, so = os.path.join(str(tmp_path), "h.cpp"), os.path.join(str(tmp_path), "h.so")
+    open(cpp, "w").write(host)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, cpp])
+    lib = ctypes.CDLL(so)
+    lib.div_n.restype, lib.div_n.argtypes = ctypes.c_double, [ctypes.c_double, ctypes.c_double]
+    lib.fkey.restype, lib.fkey.argtypes = ctypes.c_int, [ctypes.c_float]
+    lib.funkey.restype, lib.funkey.argtypes = ctypes.c_float, [ctypes.c_int]
+    rng = np.random.default_rng(5)
+    sizes = sorted({kh * kw for kh in range(1, 26, 2) for kw in range(3, 26, 2)})
+    for c in np.concatenate([rng.uniform(0, 4000 * 625, 200), rng.standard_normal(200) * 10.0 ** rng.integers(-6, 9, 200)]):
+        for n in sizes:
+            assert lib.div_n(float(c), float(n)) == c / n, (c, n)
+    vals = np.concatenate([rng.standard_normal(2000).astype(np.float32) * np.float32(10.0) ** rng.integers(-20, 20, 2000).astype(np.float32),
+                           np.array([0.0, -0.0, np.inf, -np.inf, 1e-45, -1e-45, 3.4028235e38, -3.4028235e38], np.float32)])
+    keys = np.array([lib.fkey(ctypes.c_float(float(v))) for v in vals], np.int64)
+    order = np.argsort(vals, kind="stable")
+    strictly = np.diff(vals[order]) > 0                           # float order == key order (-0.0 and 0.0 compare equal
+    assert (np.diff(keys[order])[strictly] > 0).all()             # and may keep either key: the sign of a zero min / max)
+    back = np.array([lib.funkey(int(k)) for k in keys], np.float32)
+    np.testing.assert_array_equal(back.view(np.int32), vals.view(np.int32))   # bit-exact round trip
