@@ -327,6 +327,20 @@ def reference_outputs():
     g["geodesic.lat2d"], g["geodesic.lon2d"] = lat2c, lon2c
     g["geodesic.slope_2d"] = geod._cpu_geodesic_slope(np.stack([gz, lat2c, lon2c]), a2, b2, 1.0)
     g["geodesic.aspect_2d"] = geod._cpu_geodesic_aspect(np.stack([gz, lat2c, lon2c]), a2, b2, 1.0)
+
+    # focal.apply over all-ones windows: the shapes of the reference's own focal benchmark
+    # (benchmarks/benchmarks/focal.py FocalApply: custom_kernel(np.ones((5, 5))) / ((25, 25))) plus a
+    # rectangular one, on a raster with NaNs, an all-NaN patch, +-inf and a FLT_MAX-style sentinel.
+    # A separate generator so that the arrays above keep their seeded values.
+    rng4 = np.random.default_rng(4040)
+    zo = terrain(rng4, 70, 96, nans=0.02)
+    zo[20:30, 40:52] = np.nan
+    zo[5, 3] = np.inf
+    zo[60, 90] = -np.inf
+    zo[44, 10] = np.float32(3.4028235e38)
+    g["apply_ones.dem"] = zo
+    for kh, kw in ((5, 5), (25, 25), (3, 7), (9, 3)):
+        g["apply_ones.mean.%dx%d" % (kh, kw)] = focal._apply_numpy(zo, np.ones((kh, kw)), focal._calc_mean)
     return g
 
 

@@ -178,6 +178,16 @@ def test_focal_apply_vs_reference(refout, mn):
                                       refout["apply.out.%s.%s" % (mn, s)], err_msg=s)
 
 
+@pytest.mark.parametrize("kh,kw", [(5, 5), (25, 25), (3, 7), (9, 3)])
+def test_focal_apply_mean_over_all_ones_windows_vs_reference(refout, kh, kw):
+    """focal.apply(raster, np.ones((kh, kw))) -- the shapes of the reference's FocalApply benchmark -- run through
+    the unmodified reference (`_apply_numpy` + `_calc_mean`) on a raster with NaNs, an all-NaN patch, +-inf and a
+    FLT_MAX-style sentinel: the oracle the GPU's NaN-skipping running box is checked against gives the same bits."""
+    ref = refout["apply_ones.mean.%dx%d" % (kh, kw)]
+    np.testing.assert_array_equal(o.focal_apply(refout["apply_ones.dem"], np.ones((kh, kw)), "mean"), ref)
+    assert np.isinf(ref).any() and (np.isnan(ref).any() or kh * kw > 120)     # the 10 x 12 all-NaN patch is smaller than 25 x 25
+
+
 def test_multispectral_vs_reference(refout):
     r = refout
     np.testing.assert_array_equal(o.normalized_ratio(r["ms.nir"], r["ms.red"]), r["ms.ndvi"])
